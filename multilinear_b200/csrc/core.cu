@@ -1,0 +1,330 @@
+// Context, memory and the array-level C ABI (field vectors, NTT, Reed-Solomon, multilinear transforms, transcript).
+#include "field.cuh"
+#include "handles.h"
+#include "internal.h"
+
+namespace mlb {
+
+static thread_local char g_err[512] = "";
+unsigned long long g_kernel_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+static std::mutex g_ctx_mu;
+static std::map<int, Ctx*> g_ctx;
+
+int get_ctx(Ctx** out) {
+    int dev = 0;
+    MLB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_ctx_mu);
+    auto it = g_ctx.find(dev);
+    if (it == g_ctx.end()) {
+        cudaDeviceProp prop;
+        MLB_CUDA(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major < 10) {
+            set_error("device %d (%s, sm_%d%d) is not a Blackwell GPU; this library ships sm_100a code only", dev, prop.name, prop.major, prop.minor);
+            return ML_ERR_CUDA;
+        }
+        Ctx* c = new Ctx();
+        c->device = dev;
+        c->sm_count = prop.multiProcessorCount;
+        MLB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        MLB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long thr = ~0ull;  // keep freed scratch cached in the pool
+        MLB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        it = g_ctx.emplace(dev, c).first;
+    }
+    *out = it->second;
+    return ML_OK;
+}
+int dev_alloc_async(void** p, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(p, bytes, s);
+    if (e != cudaSuccess) { set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); return ML_ERR_ALLOC; }
+    return ML_OK;
+}
+int dev_free_async(void* p, cudaStream_t s) {
+    if (p) MLB_CUDA(cudaFreeAsync(p, s));
+    return ML_OK;
+}
+
+// RAII scratch buffer on a stream
+struct Scratch {
+    void* p = nullptr;
+    cudaStream_t s;
+    explicit Scratch(cudaStream_t st) : s(st) {}
+    int alloc(size_t bytes) { return dev_alloc_async(&p, bytes, s); }
+    ~Scratch() { if (p) cudaFreeAsync(p, s); }
+    template <class T> T* as() { return (T*)p; }
+};
+
+}  // namespace mlb
+
+using namespace mlb;
+
+#define API_BEGIN   \
+    Ctx* ctx;       \
+    MLB_TRY(get_ctx(&ctx));
+#define ST(stream_arg) ((cudaStream_t)(stream_arg))
+
+extern "C" {
+
+const char* ml_last_error(void) { return g_err; }
+const char* ml_version(void) { return "multilinear_b200 0.1 (sm_100a)"; }
+int ml_device_count(int* count) { MLB_CUDA(cudaGetDeviceCount(count)); return ML_OK; }
+int ml_set_device(int device) { MLB_CUDA(cudaSetDevice(device)); return ML_OK; }
+int ml_device_name(char* out, size_t cap) {
+    int dev;
+    MLB_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    MLB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    snprintf(out, cap, "%s", prop.name);
+    return ML_OK;
+}
+int ml_synchronize(void) { MLB_CUDA(cudaDeviceSynchronize()); return ML_OK; }
+uint64_t ml_kernel_launches(void) { return g_kernel_launches; }
+
+int ml_dev_alloc(size_t bytes, void** out) { MLB_CUDA(cudaMalloc(out, bytes ? bytes : 16)); return ML_OK; }
+int ml_dev_free(void* p) { MLB_CUDA(cudaFree(p)); return ML_OK; }
+int ml_dev_upload(void* dst, const void* src, size_t bytes) { MLB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return ML_OK; }
+int ml_dev_download(void* dst, const void* src, size_t bytes) { MLB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return ML_OK; }
+int ml_host_alloc_pinned(size_t bytes, void** out) { MLB_CUDA(cudaMallocHost(out, bytes ? bytes : 16)); return ML_OK; }
+int ml_host_free_pinned(void* p) { MLB_CUDA(cudaFreeHost(p)); return ML_OK; }
+
+// ------------------------------------------------------------------ helpers for host-pointer entry points
+static int upload(Scratch& sc, const void* host, size_t bytes, cudaStream_t s) {
+    MLB_TRY(sc.alloc(bytes));
+    if (bytes) MLB_CUDA(cudaMemcpyAsync(sc.p, host, bytes, cudaMemcpyHostToDevice, s));
+    return ML_OK;
+}
+static int download(void* host, const void* dev, size_t bytes, cudaStream_t s) {
+    if (bytes) MLB_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s));
+    MLB_CUDA(cudaStreamSynchronize(s));
+    return ML_OK;
+}
+
+// ------------------------------------------------------------------ field vectors
+static int vec2(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+    API_BEGIN
+    cudaStream_t s = ctx->stream;
+    Scratch da(s), db(s), dout(s);
+    MLB_TRY(upload(da, a, n * 16, s));
+    if (b) MLB_TRY(upload(db, b, n * 16, s));
+    MLB_TRY(dout.alloc(n * 16));
+    MLB_TRY(fe_vec_launch(op, da.as<fe>(), db.as<fe>(), n, dout.as<fe>(), s));
+    return download(out, dout.p, n * 16, s);
+}
+int ml_fe_add_vec(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) { return vec2(0, a, b, n, out); }
+int ml_fe_sub_vec(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) { return vec2(1, a, b, n, out); }
+int ml_fe_mul_vec(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) { return vec2(2, a, b, n, out); }
+int ml_fe_inv_vec(const uint8_t* a, size_t n, uint8_t* out) { return vec2(3, a, nullptr, n, out); }
+int ml_fe_pow_vec(const uint8_t* a, const uint8_t exp_le[16], size_t n, uint8_t* out) {
+    API_BEGIN
+    cudaStream_t s = ctx->stream;
+    Scratch da(s), dout(s);
+    MLB_TRY(upload(da, a, n * 16, s));
+    MLB_TRY(dout.alloc(n * 16));
+    MLB_TRY(fe_pow_vec_launch(da.as<fe>(), hfe_load(exp_le), n, dout.as<fe>(), s));
+    return download(out, dout.p, n * 16, s);
+}
+int ml_fe_from_i64_vec(const int64_t* v, size_t n, uint8_t* out) {
+    API_BEGIN
+    cudaStream_t s = ctx->stream;
+    Scratch dv(s), dout(s);
+    MLB_TRY(upload(dv, v, n * 8, s));
+    MLB_TRY(dout.alloc(n * 16));
+    MLB_TRY(fe_from_i64_launch(dv.as<int64_t>(), n, dout.as<fe>(), s));
+    return download(out, dout.p, n * 16, s);
+}
+int ml_synthetic_elements_dev(uint64_t seed, size_t n, void* out_dev, void* stream) {
+    API_BEGIN
+    (void)ctx;
+    return synthetic_launch(seed, n, (fe*)out_dev, ST(stream));
+}
+
+// ------------------------------------------------------------------ NTT
+int ml_pow2_generator(uint64_t log_size, uint8_t out[16]) {
+    hfe g;
+    if (!hfe_pow2_generator(log_size, &g)) { set_error("pow_2_generator(%llu): None", (unsigned long long)log_size); return ML_ERR_OUT_OF_RANGE; }
+    hfe_store(out, g);
+    return ML_OK;
+}
+int ml_pow2_generator_powers_dev(uint64_t log_size, void* out_dev, void* stream) {
+    API_BEGIN
+    if (log_size > 40) { set_error("pow_2_generator_powers(%llu): None", (unsigned long long)log_size); return ML_ERR_OUT_OF_RANGE; }
+    return powers_launch(ctx, (int)log_size, (fe*)out_dev, ST(stream));
+}
+int ml_pow2_generator_powers(uint64_t log_size, uint8_t* out) {
+    API_BEGIN
+    if (log_size > 40) { set_error("pow_2_generator_powers(%llu): None", (unsigned long long)log_size); return ML_ERR_OUT_OF_RANGE; }
+    cudaStream_t s = ctx->stream;
+    Scratch d(s);
+    const size_t bytes = ((size_t)16) << log_size;
+    MLB_TRY(d.alloc(bytes));
+    MLB_TRY(powers_launch(ctx, (int)log_size, d.as<fe>(), s));
+    return download(out, d.p, bytes, s);
+}
+int ml_bit_reverse_permutation(uint8_t* values, size_t n, size_t elem_bytes) {
+    API_BEGIN
+    if (n == 0) return ML_OK;
+    if (elem_bytes != 16) { set_error("bit_reverse_permutation: only 16-byte (Field128) elements are supported"); return ML_ERR_ARG; }
+    cudaStream_t s = ctx->stream;
+    Scratch din(s), dout(s);
+    MLB_TRY(upload(din, values, n * 16, s));
+    MLB_TRY(dout.alloc(n * 16));
+    MLB_TRY(bit_reverse_launch(din.p, dout.p, n, 16, s));
+    return download(values, dout.p, n * 16, s);
+}
+
+// gen must be the primitive n-th root the reference's callers pass (pow_2_generator(log2 n)) or its inverse
+static int classify_gen(size_t n, const uint8_t gen[16], bool* use_inverse_tables) {
+    const unsigned log_n = ilog2(n);
+    hfe g = hfe_load(gen), w;
+    if (log_n > 40 || !hfe_pow2_generator(log_n, &w)) { set_error("no root of unity of order 2^%u", log_n); return ML_ERR_OUT_OF_RANGE; }
+    if (g == w) { *use_inverse_tables = false; return ML_OK; }
+    if (n > 1 && g == hfe_inv(w)) { *use_inverse_tables = true; return ML_OK; }
+    set_error("ntt: gen is not pow_2_generator(%u) or its inverse", log_n);
+    return ML_ERR_GENERATOR;
+}
+static int ntt_dev_impl(Ctx* ctx, const void* in, size_t n, const uint8_t gen[16], void* out, bool is_intt, bool rs, cudaStream_t s) {
+    const size_t N = rs ? n << ML_LOG_BLOWUP : n;
+    if (!is_pow2(N)) { set_error("The number of coeffs must be a power of 2"); return ML_ERR_NOT_POW2; }
+    bool inv_tables;
+    MLB_TRY(classify_gen(N, gen, &inv_tables));
+    // intt(gen) runs the network with 1/gen and scales by 1/n; with gen = w^-1 that is the forward tables plus scaling
+    if (!is_intt) {
+        if (!inv_tables) return ntt_launch(ctx, (const fe*)in, (fe*)out, (int)ilog2(N), false, rs, s);
+        // forward network with the inverse root = unscaled inverse transform: run inverse tables then multiply by N
+        MLB_TRY(ntt_launch(ctx, (const fe*)in, (fe*)out, (int)ilog2(N), true, rs, s));
+        // scale back by N: out[i] *= N  (rare path: callers normally pass the forward generator)
+        hfe Nf = hfe_new((hfe)N);
+        Scratch tmp(s);
+        MLB_TRY(tmp.alloc(16));
+        uint8_t nb[16];
+        hfe_store(nb, Nf);
+        MLB_CUDA(cudaMemcpyAsync(tmp.p, nb, 16, cudaMemcpyHostToDevice, s));
+        return fe_vec_launch(4, (const fe*)out, tmp.as<fe>(), N, (fe*)out, s);
+    }
+    if (!inv_tables) return ntt_launch(ctx, (const fe*)in, (fe*)out, (int)ilog2(N), true, false, s);
+    // intt with gen = w^-1: network runs with w, then 1/n scaling
+    MLB_TRY(ntt_launch(ctx, (const fe*)in, (fe*)out, (int)ilog2(N), false, false, s));
+    hfe ninv = hfe_inv(hfe_new((hfe)N));
+    Scratch tmp(s);
+    MLB_TRY(tmp.alloc(16));
+    uint8_t nb[16];
+    hfe_store(nb, ninv);
+    MLB_CUDA(cudaMemcpyAsync(tmp.p, nb, 16, cudaMemcpyHostToDevice, s));
+    return fe_vec_launch(4, (const fe*)out, tmp.as<fe>(), N, (fe*)out, s);
+}
+int ml_ntt_dev(const void* c, size_t n, const uint8_t gen[16], void* e, void* stream) {
+    API_BEGIN
+    return ntt_dev_impl(ctx, c, n, gen, e, false, false, ST(stream));
+}
+int ml_intt_dev(const void* e, size_t n, const uint8_t gen[16], void* c, void* stream) {
+    API_BEGIN
+    return ntt_dev_impl(ctx, e, n, gen, c, true, false, ST(stream));
+}
+int ml_reed_solomon_dev(const void* c, size_t n, const uint8_t gen[16], void* code, void* stream) {
+    API_BEGIN
+    return ntt_dev_impl(ctx, c, n, gen, code, false, true, ST(stream));
+}
+static int ntt_host(const uint8_t* in, size_t n, const uint8_t gen[16], uint8_t* out, bool is_intt, bool rs) {
+    API_BEGIN
+    cudaStream_t s = ctx->stream;
+    const size_t N = rs ? n << ML_LOG_BLOWUP : n;
+    if (!is_pow2(N)) { set_error("The number of coeffs must be a power of 2"); return ML_ERR_NOT_POW2; }
+    Scratch din(s), dout(s);
+    MLB_TRY(upload(din, in, n * 16, s));
+    MLB_TRY(dout.alloc(N * 16));
+    MLB_TRY(ntt_dev_impl(ctx, din.p, n, gen, dout.p, is_intt, rs, s));
+    return download(out, dout.p, N * 16, s);
+}
+int ml_ntt(const uint8_t* c, size_t n, const uint8_t gen[16], uint8_t* e) { return ntt_host(c, n, gen, e, false, false); }
+int ml_intt(const uint8_t* e, size_t n, const uint8_t gen[16], uint8_t* c) { return ntt_host(e, n, gen, c, true, false); }
+int ml_reed_solomon(const uint8_t* c, size_t n, const uint8_t gen[16], uint8_t* code) { return ntt_host(c, n, gen, code, false, true); }
+int ml_poly_evaluate(const uint8_t* coeffs, size_t n, const uint8_t x[16], uint8_t out[16]) {
+    API_BEGIN
+    cudaStream_t s = ctx->stream;
+    Scratch d(s);
+    MLB_TRY(upload(d, coeffs, n * 16, s));
+    hfe r;
+    MLB_TRY(poly_eval_launch(ctx, d.as<fe>(), n, hfe_load(x), &r, s));
+    hfe_store(out, r);
+    return ML_OK;
+}
+
+// ------------------------------------------------------------------ multilinear polynomials
+int ml_mle_to_coefficient_dev(const void* e, size_t len, void* c, void* stream) {
+    API_BEGIN
+    (void)ctx;
+    return mobius_launch((const fe*)e, (fe*)c, len, true, ST(stream));
+}
+int ml_mle_to_evaluation_dev(const void* c, size_t len, void* e, void* stream) {
+    API_BEGIN
+    (void)ctx;
+    return mobius_launch((const fe*)c, (fe*)e, len, false, ST(stream));
+}
+static int mobius_host(const uint8_t* in, size_t len, uint8_t* out, bool sub) {
+    API_BEGIN
+    cudaStream_t s = ctx->stream;
+    Scratch d(s);
+    MLB_TRY(upload(d, in, len * 16, s));
+    MLB_TRY(mobius_launch(d.as<fe>(), d.as<fe>(), len, sub, s));
+    return download(out, d.p, len * 16, s);
+}
+int ml_mle_to_coefficient(const uint8_t* e, size_t len, uint8_t* c) { return mobius_host(e, len, c, true); }
+int ml_mle_to_evaluation(const uint8_t* c, size_t len, uint8_t* e) { return mobius_host(c, len, e, false); }
+static int load_args(const uint8_t* args, size_t n, std::vector<hfe>& v) {
+    v.resize(n);
+    for (size_t i = 0; i < n; i++) v[i] = hfe_load(args + 16 * i);
+    return ML_OK;
+}
+int ml_mle_evals_evaluate_dev(const void* evals, size_t len, const uint8_t* args, size_t n_args, uint8_t out[16], void* stream) {
+    API_BEGIN
+    std::vector<hfe> a;
+    load_args(args, n_args, a);
+    hfe r;
+    MLB_TRY(mle_evals_evaluate_launch(ctx, (const fe*)evals, len, a.data(), n_args, &r, ST(stream)));
+    hfe_store(out, r);
+    return ML_OK;
+}
+int ml_mle_evals_evaluate(const uint8_t* evals, size_t len, const uint8_t* args, size_t n_args, uint8_t out[16]) {
+    API_BEGIN
+    cudaStream_t s = ctx->stream;
+    Scratch d(s);
+    MLB_TRY(upload(d, evals, len * 16, s));
+    return ml_mle_evals_evaluate_dev(d.p, len, args, n_args, out, s);
+}
+int ml_mle_coeffs_evaluate(const uint8_t* coeffs, size_t len, const uint8_t* args, size_t n_args, uint8_t out[16]) {
+    API_BEGIN
+    cudaStream_t s = ctx->stream;
+    Scratch d(s);
+    MLB_TRY(upload(d, coeffs, len * 16, s));
+    std::vector<hfe> a;
+    load_args(args, n_args, a);
+    hfe r;
+    MLB_TRY(mle_coeffs_evaluate_launch(ctx, d.as<fe>(), len, a.data(), n_args, &r, s));
+    hfe_store(out, r);
+    return ML_OK;
+}
+
+// ------------------------------------------------------------------ transcript (host; src/transcript.rs)
+int ml_transcript_new(ml_transcript** out) { *out = new ml_transcript(); return ML_OK; }
+int ml_transcript_clone(const ml_transcript* t, ml_transcript** out) { *out = new ml_transcript(*t); return ML_OK; }
+void ml_transcript_free(ml_transcript* t) { delete t; }
+int ml_transcript_absorb(ml_transcript* t, const uint8_t* bytes, size_t len) { t->sha.update(bytes, len); return ML_OK; }
+int ml_transcript_random(const ml_transcript* t, uint8_t out[32]) { t->sha.digest(out); return ML_OK; }
+int ml_transcript_next_challenge(ml_transcript* t, uint8_t out[16]) {
+    uint8_t d[32];
+    t->sha.digest(d);
+    hfe_store(out, hfe_new(hfe_load(d)));
+    return ML_OK;
+}
+
+}  // extern "C"

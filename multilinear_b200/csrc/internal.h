@@ -1,0 +1,155 @@
+// Internal declarations shared by the .cu translation units of libmultilinear_b200.so.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/multilinear_b200.h"
+
+namespace mlb {
+
+// ------------------------------------------------------------------ errors / launch accounting
+void set_error(const char* fmt, ...);
+extern unsigned long long g_kernel_launches;
+#define MLB_COUNT_LAUNCH() (++::mlb::g_kernel_launches)
+
+#define MLB_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            ::mlb::set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #expr); \
+            return ML_ERR_CUDA;                                                                 \
+        }                                                                                       \
+    } while (0)
+#define MLB_TRY(expr)                  \
+    do {                               \
+        int _st = (expr);              \
+        if (_st != ML_OK) return _st;  \
+    } while (0)
+#define MLB_KERNEL_CHECK()                                                                      \
+    do {                                                                                        \
+        MLB_COUNT_LAUNCH();                                                                     \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess) {                                                                \
+            ::mlb::set_error("kernel launch failed: %s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return ML_ERR_CUDA;                                                                 \
+        }                                                                                       \
+    } while (0)
+
+// ------------------------------------------------------------------ host scalar field (transcript challenges,
+// round polynomials, root-of-unity parameters).  Scalars only: all array work is on the GPU.
+typedef unsigned __int128 hfe;
+static const hfe HFE_M = ((((hfe)0xFFFFFFFFFFFFFFFFULL) << 64) | (hfe)0xFFFFD30000000001ULL);
+static const uint64_t HFE_C = 0x2CFFFFFFFFFFULL;
+
+static inline hfe hfe_new(hfe x) { return x >= HFE_M ? x - HFE_M : x; }
+static inline hfe hfe_from_i64(int64_t v) { return hfe_new((hfe)(__int128)v); }
+static inline hfe hfe_load(const uint8_t* p) { hfe x; memcpy(&x, p, 16); return x; }
+static inline void hfe_store(uint8_t* p, hfe x) { memcpy(p, &x, 16); }
+static inline hfe hfe_add(hfe a, hfe b) { hfe s = a + b; return (s < a || s >= HFE_M) ? s - HFE_M : s; }
+static inline hfe hfe_sub(hfe a, hfe b) { return a >= b ? a - b : a + (HFE_M - b); }
+static inline hfe hfe_neg(hfe a) { return a ? HFE_M - a : 0; }
+static inline hfe hfe_mul(hfe a, hfe b) {
+    uint64_t a0 = (uint64_t)a, a1 = (uint64_t)(a >> 64), b0 = (uint64_t)b, b1 = (uint64_t)(b >> 64);
+    hfe p00 = (hfe)a0 * b0, p01 = (hfe)a0 * b1, p10 = (hfe)a1 * b0, p11 = (hfe)a1 * b1;
+    hfe mid = (p00 >> 64) + (uint64_t)p01 + (uint64_t)p10;
+    hfe lo = ((hfe)(uint64_t)mid << 64) | (uint64_t)p00;
+    hfe hi = p11 + (p01 >> 64) + (p10 >> 64) + (mid >> 64);
+    while (hi) {  // fold 2^128 == c
+        hfe q0 = (hfe)(uint64_t)hi * HFE_C, q1 = (hfe)(uint64_t)(hi >> 64) * HFE_C;
+        hfe t = q0 + (q1 << 64);
+        hfe nhi = (q1 >> 64) + (t < q0);
+        hfe s = lo + t;
+        nhi += (s < lo);
+        lo = s;
+        hi = nhi;
+    }
+    return hfe_new(lo);
+}
+static inline hfe hfe_pow(hfe b, hfe e) {
+    hfe r = 1;
+    while (e) { if (e & 1) r = hfe_mul(r, b); b = hfe_mul(b, b); e >>= 1; }
+    return r;
+}
+static inline hfe hfe_inv(hfe a) { return a ? hfe_pow(a, HFE_M - 2) : 0; }
+static inline hfe hfe_div(hfe a, hfe b) { return hfe_mul(a, hfe_inv(b)); }
+static inline hfe hfe_half(hfe a) { return hfe_mul(a, (HFE_M + 1) >> 1); }
+// NttField::pow_2_generator (src/ntt/mod.rs:42-54); returns false for log_size > 40
+static inline bool hfe_pow2_generator(uint64_t log_size, hfe* out) {
+    if (log_size > 40) return false;
+    *out = hfe_pow(3, (HFE_M - 1) >> log_size);
+    return true;
+}
+static inline bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
+static inline unsigned ilog2(size_t n) { return 63u - (unsigned)__builtin_clzll((unsigned long long)n); }
+
+struct fe;  // device element (field.cuh)
+
+// ------------------------------------------------------------------ per-device context
+// Root-of-unity tables for one domain size N = 2^log_n, generator w = pow_2_generator(log_n):
+//   lo[i]  = w^i              i < 2^LO_BITS (or N if smaller)
+//   hi[i]  = w^(i << LO_BITS) i < N >> LO_BITS
+//   lo_ninv[i] = lo[i] / N    (inverse transforms fold the 1/N scaling into the inter-pass twiddle)
+// so w^e = hi[e >> LO_BITS] * lo[e & mask] for any e < N, and w^-e = w^(N-e).
+static const int LO_BITS = 12;
+struct RootTables {
+    int log_n = 0;
+    fe* lo = nullptr;
+    fe* hi = nullptr;
+    fe* lo_ninv = nullptr;
+    hfe gen = 0;
+};
+struct Ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;  // library stream for host-pointer entry points
+    std::map<int, RootTables> roots;
+    fe* small_fwd = nullptr;  // w_4096^i, i < 2048   (in-tile twiddles for every pass radix <= 4096)
+    fe* small_inv = nullptr;  // w_4096^-i
+    int sm_count = 148;
+};
+int get_ctx(Ctx** out);  // context of the current device (lazily created)
+int get_root_tables(Ctx* ctx, int log_n, cudaStream_t s, const RootTables** out);
+
+// stream-ordered scratch allocation
+int dev_alloc_async(void** p, size_t bytes, cudaStream_t s);
+int dev_free_async(void* p, cudaStream_t s);
+
+// ------------------------------------------------------------------ kernels (launchers)
+// ntt.cu
+int ntt_launch(Ctx* ctx, const fe* in, fe* out, int log_n, bool inverse, bool rs_zero_padded, cudaStream_t s);
+int powers_launch(Ctx* ctx, int log_n, fe* out, cudaStream_t s);
+int bit_reverse_launch(const void* in, void* out, size_t n, size_t elem_bytes, cudaStream_t s);
+// field_ops.cu
+int fe_vec_launch(int op, const fe* a, const fe* b, size_t n, fe* out, cudaStream_t s);
+int fe_pow_vec_launch(const fe* a, hfe e, size_t n, fe* out, cudaStream_t s);
+int fe_from_i64_launch(const int64_t* v, size_t n, fe* out, cudaStream_t s);
+int synthetic_launch(uint64_t seed, size_t n, fe* out, cudaStream_t s);
+// mle.cu
+int mobius_launch(const fe* in, fe* out, size_t len, bool subtract, cudaStream_t s);
+int mle_evals_evaluate_launch(Ctx* ctx, const fe* evals, size_t len, const hfe* args, size_t n_args, hfe* out, cudaStream_t s);
+int mle_coeffs_evaluate_launch(Ctx* ctx, const fe* coeffs, size_t len, const hfe* args, size_t n_args, hfe* out, cudaStream_t s);
+int eq_table_launch(Ctx* ctx, const hfe* inputs, size_t n_vars, fe* delta, cudaStream_t s);
+int poly_eval_launch(Ctx* ctx, const fe* coeffs, size_t n, hfe x, hfe* out, cudaStream_t s);
+// merkle.cu — digests buffer holds all layers back to back: layer l starts at digest index 2L - (2L >> l)
+static inline size_t merkle_layer_offset(size_t n_leaves, size_t layer) { return 2 * n_leaves - ((2 * n_leaves) >> layer); }
+int merkle_rs_launch(const fe* code, size_t n_code, uint8_t* digests, cudaStream_t s);  // leaves (code[i], code[i+n/2])
+int merkle_bytes_launch(const uint8_t* const* data_dev_ptrs, size_t n_batches, size_t item_bytes, size_t n_items, uint8_t* digests, cudaStream_t s);
+int merkle_batched_rs_launch(const fe* const* codes_dev_ptrs, size_t n_codes, size_t n_code, uint8_t* digests, cudaStream_t s);
+int merkle_batched_pairs_launch(const uint8_t* const* pairs_dev_ptrs, size_t n_codes, size_t n_leaves, uint8_t* digests, cudaStream_t s);
+int merkle_upper_launch(uint8_t* digests, size_t n_leaves, cudaStream_t s);  // layers 1.. from layer 0
+// fri.cu
+int fri_fold_launch(Ctx* ctx, const fe* cur, size_t n_cur, fe* next, hfe r, size_t k, int log_n0, cudaStream_t s);
+int fri_batched_fold_launch(Ctx* ctx, const fe* const* codes_dev_ptrs, size_t n_codes, size_t n, fe* next, hfe fingerprint_r, hfe r, int log_n0, cudaStream_t s);
+int fingerprint_rows_launch(const fe* const* polys_dev_ptrs, size_t n_polys, size_t n, hfe r, fe* out, cudaStream_t s);
+// sumcheck.cu
+int sumcheck_sums_launch(Ctx* ctx, const fe* m, const fe* d, size_t height, hfe* s1, hfe* s2, cudaStream_t s);
+int sumcheck_partial_sum_launch(Ctx* ctx, const fe* m, const fe* d, size_t height, hfe r, hfe* out, cudaStream_t s);
+int sumcheck_fold_launch(fe* m, fe* d, size_t height, hfe r, cudaStream_t s);
+
+}  // namespace mlb

@@ -1,0 +1,204 @@
+// SHA-256 Merkle trees (src/merkle_tree/mod.rs:65-131) on sm_100a.
+//
+// Reference: leaf_i = SHA-256(bytes(data[i])) (:71, :178-182), node = SHA-256(left || right) (:184-189), every
+// layer retained (:8-11).  FRI leaves are ReedSolomonPairs (code[i], code[i + n/2]) (src/fri/mod.rs:45-55).
+//
+// Hashing is integer-pipe bound (about 1.4k alu-pipe instructions per compression), so the kernels are built to
+// keep every lane busy and every digest in registers:
+//   - one thread owns 2^G consecutive leaves and walks its own subtree with a G-deep digest stack: all
+//     2^G leaf hashes and 2^G - 1 node hashes run back to back with no shared memory, no barrier and no idle
+//     lanes (a shared-memory reduction tree idles half the lanes per level);
+//   - every layer is still written to HBM (the prover opens paths from them), 32 B per digest, once;
+//   - upper layers repeat the same scheme on digests; the last <= 2048 nodes finish in one CTA.
+// All layers live in one buffer: layer l starts at digest index 2L - (2L >> l) (merkle_layer_offset).
+#include "field.cuh"
+#include "internal.h"
+#include "sha256.cuh"
+
+namespace mlb {
+
+__device__ __forceinline__ uint8_t* layer_ptr(uint8_t* digests, size_t n_leaves, int layer, size_t idx) {
+    return digests + 32 * ((2 * n_leaves - ((2 * n_leaves) >> layer)) + idx);
+}
+
+// Push digest h of node `idx` at `layer` up a thread-private stack; j = index within the thread's group.
+template <int LOG_G>
+__device__ __forceinline__ void subtree_push(uint32_t (&stack)[LOG_G > 0 ? LOG_G : 1][8], uint32_t h[8], int j, uint8_t* digests,
+                                             size_t n_leaves, int base_layer, size_t idx) {
+#pragma unroll
+    for (int lvl = 0; lvl < LOG_G; lvl++) {
+        if ((j >> lvl) & 1) {
+            uint32_t o[8];
+            sha256_node64(stack[lvl], h, o);
+#pragma unroll
+            for (int w = 0; w < 8; w++) h[w] = o[w];
+            idx >>= 1;
+            sha_store_digest(layer_ptr(digests, n_leaves, base_layer + lvl + 1, idx), h);
+        } else {
+#pragma unroll
+            for (int w = 0; w < 8; w++) stack[lvl][w] = h[w];
+            break;
+        }
+    }
+}
+
+// Leaves = RS pairs of a code of n_code = 2 * n_leaves elements.  Thread g hashes leaves [g*2^G, (g+1)*2^G).
+template <int LOG_G>
+__global__ void __launch_bounds__(128) merkle_rs_kernel(const fe* __restrict__ code, size_t n_leaves, uint8_t* __restrict__ digests) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((g << LOG_G) >= n_leaves) return;
+    uint32_t stack[LOG_G > 0 ? LOG_G : 1][8];
+#pragma unroll
+    for (int j = 0; j < (1 << LOG_G); j++) {
+        const size_t i = (g << LOG_G) + j;
+        uint32_t m[8], h[8];
+        sha_words_from_le(__ldg(reinterpret_cast<const uint4*>(code + i)), m);
+        sha_words_from_le(__ldg(reinterpret_cast<const uint4*>(code + i + n_leaves)), m + 4);
+        sha256_leaf32(m, h);
+        sha_store_digest(layer_ptr(digests, n_leaves, 0, i), h);
+        subtree_push<LOG_G>(stack, h, j, digests, n_leaves, 0, i);
+    }
+}
+
+// Thread g reads 2^G consecutive digests of `from_layer` and writes the G layers above them.
+template <int LOG_G>
+__global__ void __launch_bounds__(128) merkle_nodes_kernel(uint8_t* __restrict__ digests, size_t n_leaves, int from_layer) {
+    const size_t count = n_leaves >> from_layer;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((g << LOG_G) >= count) return;
+    uint32_t stack[LOG_G > 0 ? LOG_G : 1][8];
+#pragma unroll
+    for (int j = 0; j < (1 << LOG_G); j++) {
+        const size_t i = (g << LOG_G) + j;
+        uint32_t h[8];
+        sha_load_digest(layer_ptr(digests, n_leaves, from_layer, i), h);
+        subtree_push<LOG_G>(stack, h, j, digests, n_leaves, from_layer, i);
+    }
+}
+
+// One CTA finishes the tree from a layer with <= 2 * blockDim.x * 4 nodes (loops otherwise).
+__global__ void __launch_bounds__(256) merkle_top_kernel(uint8_t* digests, size_t n_leaves, int from_layer) {
+    size_t count = n_leaves >> from_layer;
+    int layer = from_layer;
+    while (count > 1) {
+        const size_t next = count >> 1;
+        for (size_t i = threadIdx.x; i < next; i += blockDim.x) {
+            uint32_t l[8], r[8], o[8];
+            sha_load_digest(layer_ptr(digests, n_leaves, layer, 2 * i), l);
+            sha_load_digest(layer_ptr(digests, n_leaves, layer, 2 * i + 1), r);
+            sha256_node64(l, r, o);
+            sha_store_digest(layer_ptr(digests, n_leaves, layer + 1, i), o);
+        }
+        __syncthreads();
+        count = next;
+        layer++;
+    }
+}
+
+// Batched leaves (Merkle::batch_commit, :110-116): leaf_i = SHA-256(pair_0(i) || pair_1(i) || ... || pair_{B-1}(i)).
+// Two 32-byte pairs fill one block, so B pairs take ceil((B+1)/2) compressions (33 for B = 64).
+// PAIRS = false: src[j] is code j (n_code elements), pair = (code[i], code[i + n_leaves]);
+// PAIRS = true : src[j] is an array of n_leaves ReedSolomonPairs (32 bytes each).
+template <bool PAIRS>
+__global__ void __launch_bounds__(128) merkle_batched_kernel(const fe* const* __restrict__ src, int n_codes, size_t n_leaves,
+                                                             uint8_t* __restrict__ digests) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_leaves) return;
+    uint32_t st[8];
+    sha_iv(st);
+    uint32_t w[16];
+    const unsigned long long bits = (unsigned long long)n_codes * 256ull;
+    for (int j = 0; j < n_codes; j += 2) {
+        const fe* c0 = src[j];
+        uint4 x0 = PAIRS ? __ldg(reinterpret_cast<const uint4*>(c0 + 2 * i)) : __ldg(reinterpret_cast<const uint4*>(c0 + i));
+        uint4 y0 = PAIRS ? __ldg(reinterpret_cast<const uint4*>(c0 + 2 * i + 1)) : __ldg(reinterpret_cast<const uint4*>(c0 + i + n_leaves));
+        sha_words_from_le(x0, w);
+        sha_words_from_le(y0, w + 4);
+        if (j + 1 < n_codes) {
+            const fe* c1 = src[j + 1];
+            uint4 x1 = PAIRS ? __ldg(reinterpret_cast<const uint4*>(c1 + 2 * i)) : __ldg(reinterpret_cast<const uint4*>(c1 + i));
+            uint4 y1 = PAIRS ? __ldg(reinterpret_cast<const uint4*>(c1 + 2 * i + 1)) : __ldg(reinterpret_cast<const uint4*>(c1 + i + n_leaves));
+            sha_words_from_le(x1, w + 8);
+            sha_words_from_le(y1, w + 12);
+        } else {  // odd batch: padding starts in the second half of the last data block
+            w[8] = 0x80000000u; w[9] = 0; w[10] = 0; w[11] = 0; w[12] = 0; w[13] = 0;
+            w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits;
+        }
+        sha_compress(st, w);
+    }
+    if ((n_codes & 1) == 0) {
+        uint32_t p[16] = {0x80000000u, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, (uint32_t)(bits >> 32), (uint32_t)bits};
+        sha_compress(st, p);
+    }
+    sha_store_digest(layer_ptr(digests, n_leaves, 0, i), st);
+}
+
+// Generic byte items (Merkle<T>::commit / batch_commit for arbitrary AsRef<[u8]> items).
+__global__ void merkle_bytes_kernel(const uint8_t* const* __restrict__ data, int n_batches, size_t item_bytes, size_t n_items,
+                                    uint8_t* __restrict__ digests) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    uint32_t st[8];
+    auto next = [&](size_t pos) -> uint8_t {
+        size_t b = pos / item_bytes, off = pos - b * item_bytes;
+        return data[b][i * item_bytes + off];
+    };
+    sha256_bytes(next, (size_t)n_batches * item_bytes, st);
+    // digests may be only 32-byte aligned relative to a 256-byte aligned base: vector stores are fine
+    sha_store_digest(layer_ptr(digests, n_items, 0, i), st);
+}
+
+// Layers above `from_layer` (which must be complete).
+static int upper_from(uint8_t* digests, size_t n_leaves, int from_layer, cudaStream_t s) {
+    int total = (int)ilog2(n_leaves);
+    int layer = from_layer;
+    while (layer < total) {
+        size_t count = n_leaves >> layer;
+        if (count <= 4096) {
+            merkle_top_kernel<<<1, 256, 0, s>>>(digests, n_leaves, layer);
+            MLB_KERNEL_CHECK();
+            return ML_OK;
+        }
+        size_t threads = count >> 3;
+        merkle_nodes_kernel<3><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(digests, n_leaves, layer);
+        MLB_KERNEL_CHECK();
+        layer += 3;
+    }
+    return ML_OK;
+}
+int merkle_upper_launch(uint8_t* digests, size_t n_leaves, cudaStream_t s) { return upper_from(digests, n_leaves, 0, s); }
+
+int merkle_rs_launch(const fe* code, size_t n_code, uint8_t* digests, cudaStream_t s) {
+    const size_t L = n_code / 2;
+    if (L == 0) return ML_ERR_NOT_POW2;
+    if (L >= 8) {
+        size_t threads = L >> 3;
+        merkle_rs_kernel<3><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(code, L, digests);
+        MLB_KERNEL_CHECK();
+        return upper_from(digests, L, 3, s);
+    }
+    merkle_rs_kernel<0><<<1, 128, 0, s>>>(code, L, digests);
+    MLB_KERNEL_CHECK();
+    return upper_from(digests, L, 0, s);
+}
+
+int merkle_batched_rs_launch(const fe* const* codes, size_t n_codes, size_t n_code, uint8_t* digests, cudaStream_t s) {
+    const size_t L = n_code / 2;
+    if (L == 0 || n_codes == 0) return ML_ERR_NOT_POW2;
+    merkle_batched_kernel<false><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(codes, (int)n_codes, L, digests);
+    MLB_KERNEL_CHECK();
+    return upper_from(digests, L, 0, s);
+}
+int merkle_batched_pairs_launch(const uint8_t* const* pairs, size_t n_codes, size_t n_leaves, uint8_t* digests, cudaStream_t s) {
+    if (n_leaves == 0 || n_codes == 0) return ML_ERR_NOT_POW2;
+    merkle_batched_kernel<true><<<(unsigned)((n_leaves + 127) / 128), 128, 0, s>>>((const fe* const*)pairs, (int)n_codes, n_leaves, digests);
+    MLB_KERNEL_CHECK();
+    return upper_from(digests, n_leaves, 0, s);
+}
+int merkle_bytes_launch(const uint8_t* const* data, size_t n_batches, size_t item_bytes, size_t n_items, uint8_t* digests, cudaStream_t s) {
+    merkle_bytes_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, s>>>(data, (int)n_batches, item_bytes, n_items, digests);
+    MLB_KERNEL_CHECK();
+    return upper_from(digests, n_items, 0, s);
+}
+
+}  // namespace mlb

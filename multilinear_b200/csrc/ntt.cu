@@ -1,0 +1,323 @@
+// NTT / INTT / Reed-Solomon encode over Field128 on sm_100a.
+//
+// Reference semantics (src/ntt/mod.rs:69-110, 132-173; src/fri/mod.rs:19-28): natural-order coefficients in,
+// natural-order evaluations X[k] = sum_j x[j] * gen^(j*k) out.  The reference does bit-reverse + radix-2 DIT
+// in place on one core; here the transform is a multi-pass ("four-step") decomposition sized for HBM + SMEM:
+//
+//   N = R_0 * R_1 * ... * R_{P-1},  each R_p <= 512 (P = 1 and R <= 4096 for small N)
+//   pass p views the array as [A][R_p][B] (A = R_0..R_{p-1}, B = R_{p+1}..R_{P-1}) and one CTA owns a tile of
+//   R_p x T elements (T contiguous columns, T*16 B >= 128 B coalesced runs, 64 KB of shared memory):
+//     1. tile -> shared memory (the RS encoder reads only the n live coefficients; the zero half is implicit)
+//     2. R_p-point DIF over the strided index, three radix-2 stages per round in registers, twiddles w_R^e from a
+//        shared-memory copy of the small-root table (no multiplies spent on twiddle generation)
+//     3. store un-bit-reversed, fused with the inter-pass twiddle w_N^(k*b*A) (two-level table, one extra multiply);
+//        the last pass instead writes natural order k = k_0 + R_0*k_1 + ... in T-element runs.
+//   The bit-reversal permutations of the reference never touch HBM; index math is checked by tools/ntt_model.py.
+#include "field.cuh"
+#include "internal.h"
+
+namespace mlb {
+
+static const int NTT_THREADS = 256;
+static const int TILE_LOG = 12;  // 4096 elements = 64 KB per CTA
+
+struct PassArgs {
+    const fe* in;
+    fe* out;
+    const fe* small;  // w_4096^(+-i), i < 2048
+    const fe* lo;     // inter-pass twiddle tables of the domain (lo may be the 1/N-scaled copy)
+    const fe* hi;
+    fe scale;         // single-pass inverse: 1/N
+    int log_n, log_r, log_t, log_a, log_b;
+    int last, inverse, zero_padded, scaled_lo, has_scale;
+    int n_passes;
+    int radix_log[4];
+};
+
+template <int NS>
+__device__ __forceinline__ void dif_round(fe* data, const fe* tw, int pitch, int log_r, int log_t, int q, int tid) {
+    // stages q .. q+NS-1 of the R-point DIF; an item is the 2^NS elements m = blk*(R>>q) + j*(R>>(q+NS)) + l of column t
+    const int log_lr = log_r - q - NS;  // l range = R >> (q+NS)
+    const int items = 1 << (log_r + log_t - NS);
+    for (int w = tid; w < items; w += NTT_THREADS) {
+        const int t = w & ((1 << log_t) - 1);
+        const int rest = w >> log_t;
+        const int l = rest & ((1 << log_lr) - 1);
+        const int blk = rest >> log_lr;
+        const int m0 = (blk << (log_r - q)) + l;
+        fe x[1 << NS];
+#pragma unroll
+        for (int j = 0; j < (1 << NS); j++) x[j] = data[(m0 + (j << log_lr)) * pitch + t];
+#pragma unroll
+        for (int u = 0; u < NS; u++) {
+            const int span = 1 << (NS - 1 - u);
+#pragma unroll
+            for (int j = 0; j < (1 << NS); j++) {
+                if (j & span) continue;
+                const int e = (((j & (span - 1)) << log_lr) + l) << (q + u);
+                fe a = x[j], b = x[j + span];
+                x[j] = fe_add(a, b);
+                fe d = fe_sub(a, b);
+                x[j + span] = e ? fe_mul(d, tw[e]) : d;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < (1 << NS); j++) data[(m0 + (j << log_lr)) * pitch + t] = x[j];
+    }
+}
+
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel(PassArgs p) {
+    extern __shared__ uint4 smem_raw[];
+    fe* data = reinterpret_cast<fe*>(smem_raw);
+    const int R = 1 << p.log_r, T = 1 << p.log_t;
+    const int pitch = T > 1 ? T + 1 : 1;
+    fe* tw = data + (size_t)R * pitch;
+    const int tid = threadIdx.x;
+    const size_t tile = blockIdx.x;
+
+    for (int i = tid; i < (R >> 1); i += NTT_THREADS) tw[i] = fe_load_nc(p.small + ((size_t)i << (12 - p.log_r)));
+
+    // ---- tile coordinates
+    size_t a = 0, bt = 0, ap = 0, k0_base = 0;
+    const int log_rb = p.log_r + p.log_b;
+    if (!p.last) {
+        const int log_tiles_b = p.log_b - p.log_t;
+        bt = tile & (((size_t)1 << log_tiles_b) - 1);
+        a = tile >> log_tiles_b;
+    } else if (p.n_passes > 1) {
+        const int log_k0_tiles = p.radix_log[0] - p.log_t;
+        k0_base = (tile & (((size_t)1 << log_k0_tiles) - 1)) << p.log_t;
+        ap = tile >> log_k0_tiles;
+    }
+    const int log_a_rest = p.log_a - (p.n_passes > 1 ? p.radix_log[0] : 0);  // log2(A / R_0)
+
+    // ---- load
+    const int tile_elems = R * T;
+    if (!p.last) {
+        const size_t base = (a << log_rb) + (bt << p.log_t);
+        for (int idx = tid; idx < tile_elems; idx += NTT_THREADS) {
+            const int t = idx & (T - 1), m = idx >> p.log_t;
+            fe v;
+            if (p.zero_padded && m >= (R >> 1)) v = fe_zero();
+            else v = fe_load_nc(p.in + base + ((size_t)m << p.log_b) + t);
+            data[m * pitch + t] = v;
+        }
+    } else {
+        for (int idx = tid; idx < tile_elems; idx += NTT_THREADS) {
+            const int m = idx & (R - 1), t = idx >> p.log_r;
+            const size_t arow = (((k0_base + t) << log_a_rest) + ap);
+            fe v;
+            if (p.zero_padded && m >= (R >> 1)) v = fe_zero();  // only when the whole transform is one pass
+            else v = fe_load_nc(p.in + (arow << p.log_r) + m);
+            data[m * pitch + t] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- R-point DIF, three stages per round
+    for (int q = 0; q < p.log_r;) {
+        const int ns = p.log_r - q >= 3 ? 3 : p.log_r - q;
+        if (ns == 3) dif_round<3>(data, tw, pitch, p.log_r, p.log_t, q, tid);
+        else if (ns == 2) dif_round<2>(data, tw, pitch, p.log_r, p.log_t, q, tid);
+        else dif_round<1>(data, tw, pitch, p.log_r, p.log_t, q, tid);
+        q += ns;
+        __syncthreads();
+    }
+
+    // ---- store (un-bit-reverse; inter-pass twiddle or natural-order scatter)
+    if (!p.last) {
+        const size_t base = (a << log_rb) + (bt << p.log_t);
+        const size_t nmask = ((size_t)1 << p.log_n) - 1;
+        for (int idx = tid; idx < tile_elems; idx += NTT_THREADS) {
+            const int t = idx & (T - 1), pos = idx >> p.log_t;
+            const size_t k = __brev((unsigned)pos) >> (32 - p.log_r);
+            const size_t b = (bt << p.log_t) + t;
+            fe v = data[pos * pitch + t];
+            size_t e = (k * b) << p.log_a;
+            if (p.inverse) e = (((size_t)1 << p.log_n) - e) & nmask;
+            if (e != 0 || p.scaled_lo) {
+                fe w = fe_load_nc(p.lo + (e & (((size_t)1 << LO_BITS) - 1)));
+                if (e >> LO_BITS) w = fe_mul(w, fe_load_nc(p.hi + (e >> LO_BITS)));
+                v = fe_mul(v, w);
+            }
+            fe_store(p.out + base + (k << p.log_b) + t, v);
+        }
+    } else {
+        // a' digits k_1..k_{P-2} (k_1 most significant) -> mid = k_1 + R_1*k_2 + ...
+        size_t mid = 0;
+        {
+            int shift_out = 0, rem = log_a_rest;
+            for (int d = 1; d < p.n_passes - 1; d++) {
+                rem -= p.radix_log[d];
+                const size_t kd = (ap >> rem) & (((size_t)1 << p.radix_log[d]) - 1);
+                mid |= kd << shift_out;
+                shift_out += p.radix_log[d];
+            }
+        }
+        const int log_r0 = p.n_passes > 1 ? p.radix_log[0] : 0;
+        for (int idx = tid; idx < tile_elems; idx += NTT_THREADS) {
+            const int t = idx & (T - 1), pos = idx >> p.log_t;
+            const size_t k = p.log_r ? (__brev((unsigned)pos) >> (32 - p.log_r)) : 0;
+            fe v = data[pos * pitch + t];
+            if (p.has_scale) v = fe_mul(v, p.scale);
+            fe_store(p.out + (k0_base + t) + (mid << log_r0) + (k << p.log_a), v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ root tables
+__global__ void root_tables_kernel(fe* lo, fe* hi, fe* lo_ninv, fe gen, fe gen_hi, fe ninv, unsigned n_lo, unsigned n_hi) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_lo) {
+        fe w = fe_pow_u64(gen, i);
+        fe_store(lo + i, w);
+        fe_store(lo_ninv + i, fe_mul(w, ninv));
+    }
+    if (i < n_hi) fe_store(hi + i, fe_pow_u64(gen_hi, i));
+}
+__global__ void small_roots_kernel(fe* fwd, fe* inv, fe w, fe winv) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2048) {
+        fe_store(fwd + i, fe_pow_u64(w, i));
+        fe_store(inv + i, fe_pow_u64(winv, i));
+    }
+}
+// pow_2_generator_powers (src/ntt/mod.rs:18-28): out[i] = hi[i >> LO_BITS] * lo[i & mask]
+__global__ void powers_kernel(fe* out, const fe* lo, const fe* hi, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        fe w = fe_load_nc(lo + (i & (((size_t)1 << LO_BITS) - 1)));
+        if (i >> LO_BITS) w = fe_mul(w, fe_load_nc(hi + (i >> LO_BITS)));
+        fe_store(out + i, w);
+    }
+}
+
+static fe to_dev_fe(hfe x) {
+    fe r;
+    r.v[0] = (uint32_t)x; r.v[1] = (uint32_t)(x >> 32); r.v[2] = (uint32_t)(x >> 64); r.v[3] = (uint32_t)(x >> 96);
+    return r;
+}
+
+int get_root_tables(Ctx* ctx, int log_n, cudaStream_t s, const RootTables** out) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ctx->small_fwd) {
+        hfe w;
+        hfe_pow2_generator(12, &w);
+        MLB_CUDA(cudaMalloc((void**)&ctx->small_fwd, 2048 * 16));
+        MLB_CUDA(cudaMalloc((void**)&ctx->small_inv, 2048 * 16));
+        small_roots_kernel<<<8, 256, 0, s>>>(ctx->small_fwd, ctx->small_inv, to_dev_fe(w), to_dev_fe(hfe_inv(w)));
+        MLB_KERNEL_CHECK();
+        MLB_CUDA(cudaStreamSynchronize(s));  // tables are shared by every stream afterwards
+    }
+    auto it = ctx->roots.find(log_n);
+    if (it == ctx->roots.end()) {
+        RootTables rt;
+        rt.log_n = log_n;
+        if (!hfe_pow2_generator((uint64_t)log_n, &rt.gen)) { set_error("no 2^%d-th root of unity", log_n); return ML_ERR_OUT_OF_RANGE; }
+        const size_t n = (size_t)1 << log_n;
+        const unsigned n_lo = (unsigned)(n < ((size_t)1 << LO_BITS) ? n : ((size_t)1 << LO_BITS));
+        const unsigned n_hi = (unsigned)(n >> LO_BITS ? n >> LO_BITS : 1);
+        MLB_CUDA(cudaMalloc((void**)&rt.lo, (size_t)n_lo * 16));
+        MLB_CUDA(cudaMalloc((void**)&rt.lo_ninv, (size_t)n_lo * 16));
+        MLB_CUDA(cudaMalloc((void**)&rt.hi, (size_t)n_hi * 16));
+        hfe gen_hi = hfe_pow(rt.gen, (hfe)1 << LO_BITS);
+        hfe ninv = hfe_inv(hfe_new((hfe)n));
+        unsigned m = n_lo > n_hi ? n_lo : n_hi;
+        root_tables_kernel<<<(m + 255) / 256, 256, 0, s>>>(rt.lo, rt.hi, rt.lo_ninv, to_dev_fe(rt.gen), to_dev_fe(gen_hi), to_dev_fe(ninv), n_lo, n_hi);
+        MLB_KERNEL_CHECK();
+        MLB_CUDA(cudaStreamSynchronize(s));
+        it = ctx->roots.emplace(log_n, rt).first;
+    }
+    *out = &it->second;
+    return ML_OK;
+}
+
+int powers_launch(Ctx* ctx, int log_n, fe* out, cudaStream_t s) {
+    const RootTables* rt;
+    MLB_TRY(get_root_tables(ctx, log_n, s, &rt));
+    const size_t n = (size_t)1 << log_n;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
+    powers_kernel<<<(unsigned)blocks, 256, 0, s>>>(out, rt->lo, rt->hi, n);
+    MLB_KERNEL_CHECK();
+    return ML_OK;
+}
+
+// Natural-order NTT of size 2^log_n with the domain generator pow_2_generator(log_n) (or its inverse, with the
+// 1/N scaling of intt).  rs_zero_padded: `in` holds N/2 coefficients, the upper half of the input is zero
+// (reed_solomon's resize, src/fri/mod.rs:24).  in == out is allowed for P == 1 only when not zero padded.
+int ntt_launch(Ctx* ctx, const fe* in, fe* out, int log_n, bool inverse, bool rs_zero_padded, cudaStream_t s) {
+    MLB_CUDA(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    const RootTables* rt;
+    MLB_TRY(get_root_tables(ctx, log_n, s, &rt));
+    if (log_n == 0) {
+        if (in != out) MLB_CUDA(cudaMemcpyAsync(out, in, 16, cudaMemcpyDeviceToDevice, s));
+        return ML_OK;
+    }
+    int n_passes = log_n <= TILE_LOG ? 1 : (log_n + 8) / 9;
+    int radix_log[4] = {0, 0, 0, 0};
+    if (n_passes > 4) { set_error("NTT size 2^%d not supported", log_n); return ML_ERR_ARG; }
+    for (int p = 0; p < n_passes; p++) radix_log[p] = log_n / n_passes + (p < log_n % n_passes ? 1 : 0);
+
+    // passes 0..P-2 are tile-in-place and run in a scratch buffer; the last pass scatters to natural order in `out`
+    fe* tmp = nullptr;
+    if (n_passes > 1) MLB_TRY(dev_alloc_async((void**)&tmp, ((size_t)16) << log_n, s));
+
+    PassArgs a;
+    memset(&a, 0, sizeof a);
+    a.small = inverse ? ctx->small_inv : ctx->small_fwd;
+    a.hi = rt->hi;
+    a.log_n = log_n;
+    a.inverse = inverse ? 1 : 0;
+    a.n_passes = n_passes;
+    for (int p = 0; p < 4; p++) a.radix_log[p] = radix_log[p];
+    int log_a = 0;
+    for (int p = 0; p < n_passes; p++) {
+        a.last = p == n_passes - 1;
+        a.in = p == 0 ? in : tmp;
+        a.out = a.last ? out : tmp;
+        a.log_r = radix_log[p];
+        a.log_a = log_a;
+        a.log_b = log_n - log_a - a.log_r;
+        a.log_t = n_passes == 1 ? 0 : TILE_LOG - a.log_r;
+        a.zero_padded = (rs_zero_padded && p == 0) ? 1 : 0;
+        a.scaled_lo = (inverse && p == 0 && n_passes > 1) ? 1 : 0;
+        a.lo = a.scaled_lo ? rt->lo_ninv : rt->lo;
+        a.has_scale = (inverse && n_passes == 1) ? 1 : 0;
+        if (a.has_scale) a.scale = to_dev_fe(hfe_inv(hfe_new((hfe)1 << log_n)));
+        const int R = 1 << a.log_r, T = 1 << a.log_t;
+        const int pitch = T > 1 ? T + 1 : 1;
+        const size_t smem = ((size_t)R * pitch + (R >> 1) + 1) * 16;
+        const size_t tiles = ((size_t)1 << log_n) >> (a.log_r + a.log_t);
+        ntt_pass_kernel<<<(unsigned)tiles, NTT_THREADS, smem, s>>>(a);
+        MLB_KERNEL_CHECK();
+        log_a += a.log_r;
+    }
+    if (tmp) MLB_TRY(dev_free_async(tmp, s));
+    return ML_OK;
+}
+
+// bit_reverse_permutation (src/ntt/mod.rs:113-123) on 16-byte elements; uses trailing_zeros(n) bits like the reference
+__global__ void bit_reverse_kernel(const uint4* in, uint4* out, size_t n, int bits) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        // the reference swaps i <-> rev(i mod 2^bits) only for i < 2^bits; any tail beyond 2^bits stays put
+        size_t j = (bits && (i >> bits) == 0) ? (size_t)(__brevll((unsigned long long)i) >> (64 - bits)) : i;
+        out[i] = in[j];
+    }
+}
+int bit_reverse_launch(const void* in, void* out, size_t n, size_t elem_bytes, cudaStream_t s) {
+    if (elem_bytes != 16) { set_error("bit_reverse: device path handles 16-byte elements"); return ML_ERR_ARG; }
+    if (n == 0) return ML_OK;
+    int bits = __builtin_ctzll((unsigned long long)n);
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    bit_reverse_kernel<<<(unsigned)blocks, 256, 0, s>>>((const uint4*)in, (uint4*)out, n, bits);
+    MLB_KERNEL_CHECK();
+    return ML_OK;
+}
+
+}  // namespace mlb

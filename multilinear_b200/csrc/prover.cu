@@ -1,0 +1,1261 @@
+// Handle-level C ABI: Merkle trees, FRI prover data and proofs, sumcheck tables, PCS / batched PCS provers.
+// Host code here is orchestration only (Fiat-Shamir transcript, 3-coefficient round polynomials, query
+// bookkeeping); every array operation is a CUDA kernel from the sibling translation units.
+#include "field.cuh"
+#include "handles.h"
+#include "internal.h"
+
+using namespace mlb;
+
+#define API_BEGIN \
+    Ctx* ctx;     \
+    MLB_TRY(get_ctx(&ctx));
+#define ST(stream_arg) ((cudaStream_t)(stream_arg))
+
+namespace {
+
+struct Scratch {
+    void* p = nullptr;
+    cudaStream_t s;
+    explicit Scratch(cudaStream_t st) : s(st) {}
+    int alloc(size_t bytes) { return dev_alloc_async(&p, bytes, s); }
+    void* release() { void* r = p; p = nullptr; return r; }
+    ~Scratch() { if (p) cudaFreeAsync(p, s); }
+    template <class T> T* as() { return (T*)p; }
+};
+
+int h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    if (bytes) MLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    return ML_OK;
+}
+int d2h_sync(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    if (bytes) MLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+    MLB_CUDA(cudaStreamSynchronize(s));
+    return ML_OK;
+}
+void absorb_fe(ml_transcript* t, hfe x) {
+    uint8_t b[16];
+    hfe_store(b, x);
+    t->sha.update(b, 16);
+}
+hfe challenge(ml_transcript* t) {  // Transcript::next_challenge, src/transcript.rs:35-38
+    uint8_t d[32];
+    t->sha.digest(d);
+    return hfe_new(hfe_load(d));
+}
+
+// ------------------------------------------------------------------ path / value gathers for openings
+struct PathJob {
+    const uint8_t* digests;         // tree digests (all layers)
+    const fe* code;                 // RS code of the tree (value = code[index], code[index + n_leaves]) or null
+    unsigned long long n_leaves, index, dig_off, val_off;
+    int depth;
+};
+__global__ void gather_paths_kernel(const PathJob* __restrict__ jobs, uint8_t* __restrict__ out) {
+    const PathJob j = jobs[blockIdx.x];
+    const int t = threadIdx.x;
+    if (t < j.depth) {  // sibling at layer t (src/merkle_tree/mod.rs:43-55)
+        const unsigned long long sib = (j.index >> t) ^ 1ull;
+        const uint4* src = reinterpret_cast<const uint4*>(j.digests + 32 * ((2 * j.n_leaves - ((2 * j.n_leaves) >> t)) + sib));
+        uint4* dst = reinterpret_cast<uint4*>(out + j.dig_off + 32ull * t);
+        dst[0] = src[0];
+        dst[1] = src[1];
+    }
+    if (j.code && t >= 62 && t < 64) {
+        const fe* src = j.code + j.index + (t == 63 ? j.n_leaves : 0);
+        *reinterpret_cast<uint4*>(out + j.val_off + 16ull * (t - 62)) = *reinterpret_cast<const uint4*>(src);
+    }
+}
+// byte items: out[b*item_bytes + k] = data[b][index*item_bytes + k]
+__global__ void gather_bytes_kernel(const uint8_t* const* __restrict__ data, int n_batches, size_t item_bytes, size_t index,
+                                    uint8_t* __restrict__ out) {
+    const size_t total = (size_t)n_batches * item_bytes;
+    for (size_t p = threadIdx.x; p < total; p += blockDim.x) {
+        size_t b = p / item_bytes, k = p - b * item_bytes;
+        out[p] = data[b][index * item_bytes + k];
+    }
+}
+// batch layer values: for query q, code b: pair (code_b[idx_q], code_b[idx_q + L]) -> out[(q*B + b)*32]
+__global__ void gather_batch_values_kernel(const fe* const* __restrict__ codes, int n_codes, size_t n_leaves,
+                                           const unsigned long long* __restrict__ indices, uint8_t* __restrict__ out) {
+    const size_t q = blockIdx.x;
+    const unsigned long long idx = indices[q];
+    for (int b = threadIdx.x; b < n_codes; b += blockDim.x) {
+        const fe* c = codes[b];
+        uint4* dst = reinterpret_cast<uint4*>(out + (q * n_codes + b) * 32);
+        dst[0] = *reinterpret_cast<const uint4*>(c + idx);
+        dst[1] = *reinterpret_cast<const uint4*>(c + idx + n_leaves);
+    }
+}
+
+void free_merkle(ml_merkle* m) {
+    if (!m) return;
+    if (m->owns_digests && m->digests) cudaFree(m->digests);
+    if (m->owns_data)
+        for (void* p : m->data) cudaFree(p);
+    if (m->data_ptrs_dev) cudaFree(m->data_ptrs_dev);
+    delete m;
+}
+int new_merkle(size_t n_leaves, ml_merkle** out) {
+    ml_merkle* m = new ml_merkle();
+    m->n_leaves = n_leaves;
+    cudaError_t e = cudaMalloc((void**)&m->digests, (2 * n_leaves) * 32);
+    if (e != cudaSuccess) { delete m; set_error("digest allocation failed: %s", cudaGetErrorString(e)); return ML_ERR_ALLOC; }
+    cudaGetDevice(&m->device);
+    *out = m;
+    return ML_OK;
+}
+int merkle_fetch_root(ml_merkle* m, cudaStream_t s) {
+    const int top = (int)ilog2(m->n_leaves);
+    return d2h_sync(m->root, m->digests + 32 * merkle_layer_offset(m->n_leaves, top), 32, s);
+}
+int merkle_set_ptrs(ml_merkle* m, cudaStream_t s) {
+    MLB_CUDA(cudaMalloc((void**)&m->data_ptrs_dev, m->data.size() * sizeof(void*)));
+    return h2d(m->data_ptrs_dev, m->data.data(), m->data.size() * sizeof(void*), s);
+}
+
+// FRI layer commit: commit_rs_code (src/fri/mod.rs:45-55) + absorb root (:71, :133)
+int fri_commit_layer(ml_fri* f, fe* code, size_t n, bool owns_code, ml_transcript* t, cudaStream_t s) {
+    ml_merkle* m;
+    MLB_TRY(new_merkle(n / 2, &m));
+    m->kind = ml_merkle::RS_CODE;
+    m->item_bytes = 32;
+    m->data.push_back(code);
+    m->owns_data = false;
+    int st = merkle_rs_launch(code, n, m->digests, s);
+    if (st == ML_OK) st = merkle_fetch_root(m, s);
+    if (st != ML_OK) { free_merkle(m); return st; }
+    t->sha.update(m->root, 32);
+    ml_fri::Layer L;
+    L.code = code; L.n = n; L.owns_code = owns_code; L.tree = m;
+    f->layers.push_back(L);
+    return ML_OK;
+}
+void free_fri(ml_fri* f) {
+    if (!f) return;
+    for (auto& L : f->layers) {
+        if (L.owns_code && L.code) cudaFree(L.code);
+        free_merkle(L.tree);
+    }
+    delete f;
+}
+// tail shared by fold_step (:116-133) and batched_fold_step (batched_fri.rs:152-180); takes ownership of `next`
+int fold_finish(ml_fri* f, fe* next, size_t half_n, ml_transcript* t, cudaStream_t s) {
+    if (half_n == ((size_t)1 << ML_LOG_BLOWUP)) {
+        uint8_t b[32];
+        int st = d2h_sync(b, next, 32, s);
+        cudaFree(next);
+        MLB_TRY(st);
+        if (memcmp(b, b + 16, 16) != 0) { set_error("not an RS code"); return ML_ERR_NOT_RS_CODE; }
+        f->last = hfe_load(b);
+        f->has_last = true;
+        t->sha.update(b, 16);
+        return ML_OK;
+    }
+    int st = fri_commit_layer(f, next, half_n, true, t, s);
+    if (st != ML_OK) cudaFree(next);
+    return st;
+}
+int fri_fold_step_impl(Ctx* ctx, ml_fri* f, size_t k, hfe r, ml_transcript* t, cudaStream_t s) {
+    if (f->layers.empty()) { set_error("fold_step on empty FriProverData"); return ML_ERR_ARG; }
+    const ml_fri::Layer& last = f->layers.back();
+    const size_t n = last.n;
+    if (n <= ((size_t)1 << ML_LOG_BLOWUP)) return ML_OK;  // :83-85
+    const size_t half_n = n >> 1;
+    if ((half_n << k) > ((size_t)1 << f->log_n0)) { set_error("fold_step: k = %zu out of range for this domain", k); return ML_ERR_ARG; }
+    fe* next;
+    MLB_CUDA(cudaMalloc((void**)&next, half_n * 16));
+    int st = fri_fold_launch(ctx, last.code, n, next, r, k, f->log_n0, s);
+    if (st != ML_OK) { cudaFree(next); return st; }
+    return fold_finish(f, next, half_n, t, s);
+}
+int fri_init_owned(ml_fri** out, fe* code, size_t n, bool owns, ml_transcript* t, cudaStream_t s) {
+    ml_fri* f = new ml_fri();
+    f->log_n0 = (int)ilog2(n);
+    int st = fri_commit_layer(f, code, n, owns, t, s);
+    if (st != ML_OK) { if (owns) cudaFree(code); free_fri(f); return st; }
+    *out = f;
+    return ML_OK;
+}
+int check_code_len(size_t n) {
+    if (!is_pow2(n) || n < 2) { set_error("Input size must be a power of two (>= 2)"); return ML_ERR_NOT_POW2; }
+    return ML_OK;
+}
+int fri_fold_all(Ctx* ctx, ml_fri* f, ml_transcript* t, cudaStream_t s) {  // :138-143
+    const size_t num_steps = (size_t)f->log_n0 - ML_LOG_BLOWUP;
+    for (size_t k = 0; k < num_steps; k++) {
+        hfe r = challenge(t);
+        MLB_TRY(fri_fold_step_impl(ctx, f, k, r, t, s));
+    }
+    if (!f->has_last) { set_error("fold: last_element is None"); return ML_ERR_SIZE; }
+    return ML_OK;
+}
+
+// ------------------------------------------------------------------ query phase
+size_t next_query_index(ml_transcript* t, size_t domain_size) {  // :269-271
+    uint8_t d[32];
+    t->sha.digest(d);
+    uint64_t v;
+    memcpy(&v, d, 8);
+    return (size_t)(v % (uint64_t)(domain_size / 2));
+}
+void absorb_index(ml_transcript* t, size_t idx) {  // :276 usize little-endian
+    uint64_t v = idx;
+    t->sha.update(&v, 8);
+}
+void fill_dirs(PathH& p, size_t index, int depth) {
+    p.dirs.resize(depth);
+    for (int l = 0; l < depth; l++) p.dirs[l] = ((index >> l) & 1) ? 0 : 1;  // even index: sibling on the Right
+}
+// open_query_at (:154-174) for many indices at once: one gather kernel, one D2H copy
+int fri_open_queries(const ml_fri* f, const std::vector<size_t>& indices, std::vector<QueryH>& out, cudaStream_t s) {
+    const size_t nq = indices.size(), nt = f->layers.size();
+    out.assign(nq, QueryH());
+    if (nq == 0 || nt == 0) return ML_OK;
+    std::vector<PathJob> jobs;
+    jobs.reserve(nq * nt);
+    size_t off = 0;
+    for (size_t q = 0; q < nq; q++) {
+        size_t cur = indices[q], cur_n = f->layers[0].n / 2;
+        out[q].paths.resize(nt);
+        for (size_t j = 0; j < nt; j++) {
+            const ml_fri::Layer& L = f->layers[j];
+            PathJob pj;
+            pj.digests = L.tree->digests; pj.code = L.code; pj.n_leaves = L.n / 2; pj.index = cur;
+            pj.depth = (int)ilog2(L.n / 2);
+            pj.val_off = off; off += 32;
+            pj.dig_off = off; off += 32ull * pj.depth;
+            jobs.push_back(pj);
+            cur_n /= 2;
+            if (cur_n) cur %= cur_n;
+        }
+    }
+    Scratch djobs(s), dout(s);
+    MLB_TRY(djobs.alloc(jobs.size() * sizeof(PathJob)));
+    MLB_TRY(dout.alloc(off));
+    MLB_TRY(h2d(djobs.p, jobs.data(), jobs.size() * sizeof(PathJob), s));
+    gather_paths_kernel<<<(unsigned)jobs.size(), 64, 0, s>>>(djobs.as<PathJob>(), dout.as<uint8_t>());
+    MLB_KERNEL_CHECK();
+    std::vector<uint8_t> host(off);
+    MLB_TRY(d2h_sync(host.data(), dout.p, off, s));
+    size_t ji = 0;
+    for (size_t q = 0; q < nq; q++)
+        for (size_t j = 0; j < nt; j++, ji++) {
+            const PathJob& pj = jobs[ji];
+            PathH& p = out[q].paths[j];
+            p.value.assign(host.begin() + pj.val_off, host.begin() + pj.val_off + 32);
+            p.digests.assign(host.begin() + pj.dig_off, host.begin() + pj.dig_off + 32ull * pj.depth);
+            fill_dirs(p, pj.index, pj.depth);
+        }
+    return ML_OK;
+}
+// the 128 query indices (:268-277): they depend on the transcript only, so derive them all before gathering
+void derive_indices(ml_transcript* t, size_t domain_size, std::vector<size_t>& idx) {
+    idx.resize(ML_NUM_QUERIES);
+    for (int q = 0; q < ML_NUM_QUERIES; q++) {
+        idx[q] = next_query_index(t, domain_size);
+        absorb_index(t, idx[q]);
+    }
+}
+int assemble_fri_proof(const ml_fri* f, size_t domain_size, ml_transcript* t, ml_fri_proof* p, cudaStream_t s) {
+    std::vector<size_t> idx;
+    derive_indices(t, domain_size, idx);
+    MLB_TRY(fri_open_queries(f, idx, p->queries, s));
+    p->commitments.resize(32 * f->layers.size());
+    for (size_t j = 0; j < f->layers.size(); j++) memcpy(&p->commitments[32 * j], f->layers[j].tree->root, 32);
+    p->last_elem = f->last;
+    t->sha.digest(p->last_random);
+    return ML_OK;
+}
+
+// ------------------------------------------------------------------ sumcheck round (host part of :174-202)
+// Lagrange interpolation over x = 0..n-1 (src/polynomials.rs:51-86), tiny n
+void interpolate(const std::vector<hfe>& evals, std::vector<hfe>& coeffs) {
+    const size_t n = evals.size();
+    coeffs.assign(n, 0);
+    for (size_t j = 0; j < n; j++) {
+        std::vector<hfe> lj(1, 1);
+        hfe denom = 1;
+        for (size_t m = 0; m < n; m++) {
+            if (m == j) continue;
+            std::vector<hfe> nl(lj.size() + 1, 0);
+            hfe xm = hfe_new((hfe)m);
+            for (size_t i = 0; i < lj.size(); i++) {
+                nl[i] = hfe_sub(nl[i], hfe_mul(lj[i], xm));
+                nl[i + 1] = hfe_add(nl[i + 1], lj[i]);
+            }
+            lj.swap(nl);
+            denom = hfe_mul(denom, hfe_sub(hfe_new((hfe)j), xm));
+        }
+        hfe scale = hfe_div(evals[j], denom);
+        for (size_t i = 0; i < n; i++) coeffs[i] = hfe_add(coeffs[i], hfe_mul(scale, lj[i]));
+    }
+}
+hfe poly_eval(const std::vector<hfe>& c, hfe x) {
+    hfe acc = 0;
+    for (size_t i = c.size(); i-- > 0;) acc = hfe_add(hfe_mul(acc, x), c[i]);
+    return acc;
+}
+int sumcheck_round(Ctx* ctx, ml_sumcheck* sc, size_t total_degree, hfe* previous_sum, ml_transcript* t, hfe* nonzero_out, hfe* r_out,
+                   cudaStream_t s) {
+    std::vector<hfe> evals(total_degree + 1, 0), coeffs;
+    if (total_degree == 2) {  // the PCS path: both partial sums in one pass over the tables
+        MLB_TRY(sumcheck_sums_launch(ctx, sc->matrix, sc->delta, sc->height, &evals[1], &evals[2], s));
+    } else {
+        for (size_t i = 1; i <= total_degree; i++)
+            MLB_TRY(sumcheck_partial_sum_launch(ctx, sc->matrix, sc->delta, sc->height, hfe_new((hfe)i), &evals[i], s));
+    }
+    if (total_degree >= 1) evals[0] = hfe_sub(*previous_sum, evals[1]);  // :188
+    else evals[0] = *previous_sum;
+    interpolate(evals, coeffs);                                           // :189-192
+    for (size_t i = 1; i <= total_degree; i++) { nonzero_out[i - 1] = coeffs[i]; absorb_fe(t, coeffs[i]); }  // :193-197
+    hfe r = challenge(t);                                                 // :198
+    *previous_sum = poly_eval(coeffs, r);                                 // :199
+    MLB_TRY(sumcheck_fold_launch(sc->matrix, sc->delta, sc->height, r, s));  // :200
+    sc->height >>= 1;
+    *r_out = r;
+    return ML_OK;
+}
+void free_sumcheck(ml_sumcheck* s) {
+    if (!s) return;
+    if (s->matrix) cudaFree(s->matrix);
+    if (s->delta) cudaFree(s->delta);
+    delete s;
+}
+int sumcheck_build(Ctx* ctx, const uint8_t* inputs, size_t n_vars, const void* evals, bool evals_on_device, size_t height, cudaStream_t s,
+                   ml_sumcheck** out) {
+    if (n_vars >= 40 || ((size_t)1 << n_vars) != height) { set_error("assert_eq!(1 << n_vars, height) failed"); return ML_ERR_SIZE; }
+    ml_sumcheck* sc = new ml_sumcheck();
+    sc->height = height;
+    if (cudaMalloc((void**)&sc->matrix, height * 16) != cudaSuccess || cudaMalloc((void**)&sc->delta, height * 16) != cudaSuccess) {
+        free_sumcheck(sc);
+        set_error("sumcheck table allocation failed");
+        return ML_ERR_ALLOC;
+    }
+    cudaError_t e = cudaMemcpyAsync(sc->matrix, evals, height * 16, evals_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { free_sumcheck(sc); set_error("copy failed: %s", cudaGetErrorString(e)); return ML_ERR_CUDA; }
+    std::vector<hfe> pts(n_vars);
+    for (size_t i = 0; i < n_vars; i++) pts[i] = hfe_load(inputs + 16 * i);
+    int st = eq_table_launch(ctx, pts.data(), n_vars, sc->delta, s);
+    if (st == ML_OK && cudaStreamSynchronize(s) != cudaSuccess) st = ML_ERR_CUDA;  // pts is a host temporary
+    if (st != ML_OK) { free_sumcheck(sc); return st; }
+    *out = sc;
+    return ML_OK;
+}
+
+// evals -> to_coefficient -> bit_reverse -> reed_solomon (multilinear_pcs.rs:101-107): returns a new owned code of 2n elements
+int encode_poly(Ctx* ctx, const fe* evals_dev, size_t n, fe** code_out, cudaStream_t s) {
+    const int log_domain = (int)ilog2(n) + ML_LOG_BLOWUP;
+    Scratch coeffs(s), rev(s);
+    MLB_TRY(coeffs.alloc(n * 16));
+    MLB_TRY(rev.alloc(n * 16));
+    MLB_TRY(mobius_launch(evals_dev, coeffs.as<fe>(), n, true, s));
+    MLB_TRY(bit_reverse_launch(coeffs.p, rev.p, n, 16, s));
+    fe* code;
+    MLB_CUDA(cudaMalloc((void**)&code, (n << ML_LOG_BLOWUP) * 16));
+    int st = ntt_launch(ctx, rev.as<fe>(), code, log_domain, false, true, s);
+    if (st != ML_OK) { cudaFree(code); return st; }
+    *code_out = code;
+    return ML_OK;
+}
+
+// ------------------------------------------------------------------ host verifiers (O(128 log n) work)
+void hash_node_host(const uint8_t* l, const uint8_t* r, uint8_t* out) {
+    HostSha256 h;
+    h.update(l, 32);
+    h.update(r, 32);
+    h.digest(out);
+}
+int path_verify(const PathH& p, const uint8_t* root, size_t index) {  // merkle_tree/mod.rs:216-246
+    uint8_t h[32], nx[32];
+    HostSha256 hs;
+    hs.update(p.value.data(), p.value.size());
+    hs.digest(h);
+    size_t computed = 0;
+    for (size_t i = 0; i < p.dirs.size(); i++) {
+        if (p.dirs[i] == 0) { computed += (size_t)1 << i; hash_node_host(&p.digests[32 * i], h, nx); }
+        else hash_node_host(h, &p.digests[32 * i], nx);
+        memcpy(h, nx, 32);
+    }
+    if (memcmp(h, root, 32) != 0) return ML_V_INCLUSION_HASH;
+    if (computed != index) return ML_V_INCLUSION_INDEX;
+    return ML_V_OK;
+}
+int query_verify(const QueryH& q, const uint8_t* commitments, size_t n_commitments, hfe last_element, size_t n, size_t index, hfe gen,
+                 const hfe* rs) {  // fri/mod.rs:184-236
+    if (q.paths.size() != n_commitments) return ML_V_WRONG_NUM_PATHS;
+    size_t cur_n = n, cur_idx = index;
+    hfe cur_gen = gen, two = 2;
+    for (size_t i = 0; i < q.paths.size(); i++) {
+        const PathH& p = q.paths[i];
+        int st = path_verify(p, commitments + 32 * i, cur_idx);
+        if (st != ML_V_OK) return st;
+        hfe value = hfe_load(p.value.data()), minus_value = hfe_load(p.value.data() + 16);
+        hfe gp = hfe_pow(cur_gen, (hfe)cur_idx);
+        hfe even = hfe_div(hfe_add(value, minus_value), two);
+        hfe odd = hfe_div(hfe_sub(value, minus_value), hfe_mul(two, gp));
+        hfe expect = hfe_add(even, hfe_mul(rs[i], odd));
+        if (i == q.paths.size() - 1) return last_element == expect ? ML_V_OK : ML_V_QUERY_MISMATCH;
+        size_t next_idx = cur_idx % (cur_n / 2);
+        const PathH& np = q.paths[i + 1];
+        hfe next_value = next_idx == cur_idx ? hfe_load(np.value.data()) : hfe_load(np.value.data() + 16);
+        if (next_value != expect) return ML_V_QUERY_MISMATCH;
+        cur_gen = hfe_mul(cur_gen, cur_gen);
+        cur_n /= 2;
+        cur_idx = next_idx;
+    }
+    return ML_V_OK;
+}
+int fri_verify_queries(const ml_fri_proof* p, ml_transcript* t, const hfe* rs) {  // fri/mod.rs:311-340
+    const size_t nc = p->commitments.size() / 32;
+    const size_t log_domain = nc + ML_LOG_BLOWUP, domain = (size_t)1 << log_domain;
+    hfe gen;
+    if (!hfe_pow2_generator(log_domain, &gen)) return ML_V_QUERY_MISMATCH;
+    for (const QueryH& q : p->queries) {
+        size_t idx = next_query_index(t, domain);
+        absorb_index(t, idx);
+        int st = query_verify(q, p->commitments.data(), nc, p->last_elem, domain / 2, idx, gen, rs);
+        if (st != ML_V_OK) return st;
+    }
+    uint8_t lr[32];
+    t->sha.digest(lr);
+    return memcmp(lr, p->last_random, 32) == 0 ? ML_V_OK : ML_V_LAST_RANDOM;
+}
+hfe delta_evaluate(const hfe* data, const hfe* points, size_t n) {  // evaluation.rs:80-90
+    hfe prod = 1;
+    for (size_t i = 0; i < n; i++) {
+        hfe a = data[i], b = points[i];
+        prod = hfe_mul(prod, hfe_add(hfe_mul(a, b), hfe_mul(hfe_sub(1, a), hfe_sub(1, b))));
+    }
+    return prod;
+}
+void to_polynomial(const hfe* nonzero, hfe sum, hfe pol[3]) {  // sumcheck.rs:269-276 (degree 2)
+    pol[0] = hfe_div(hfe_sub(sum, hfe_add(nonzero[0], nonzero[1])), 2);
+    pol[1] = nonzero[0];
+    pol[2] = nonzero[1];
+}
+hfe eval3(const hfe pol[3], hfe x) { return hfe_add(hfe_mul(hfe_add(hfe_mul(pol[2], x), pol[1]), x), pol[0]); }
+int sumcheck_replay(const std::vector<hfe>& sc, hfe sum, const std::vector<hfe>& inputs, const std::vector<hfe>& rs, hfe last_elem) {
+    const size_t n = rs.size();
+    hfe pol[3];
+    to_polynomial(&sc[0], sum, pol);
+    for (size_t i = 1; i < n; i++) to_polynomial(&sc[2 * i], eval3(pol, rs[i - 1]), pol);
+    hfe delta = delta_evaluate(inputs.data(), rs.data(), n);
+    return hfe_mul(delta, last_elem) == eval3(pol, rs[n - 1]) ? ML_V_OK : ML_V_SUMCHECK;
+}
+hfe fingerprint_host(hfe r, const hfe* c, size_t n) {  // batched_fri.rs:30-38
+    hfe acc = 0;
+    for (size_t i = 0; i < n; i++) acc = hfe_add(hfe_mul(acc, r), c[i]);
+    return acc;
+}
+
+// ------------------------------------------------------------------ wire format (bincode fixed-int LE via serde, fri/mod.rs:367-369)
+struct Writer {
+    uint8_t* p;
+    size_t n = 0;
+    explicit Writer(uint8_t* out) : p(out) {}
+    void bytes(const void* b, size_t len) { if (p) memcpy(p + n, b, len); n += len; }
+    void u64(uint64_t v) { bytes(&v, 8); }
+    void u32(uint32_t v) { bytes(&v, 4); }
+    void febytes(const uint8_t* b) { u64(16); bytes(b, 16); }  // Field128::serialize -> serialize_bytes (field.rs:40-48)
+    void pair(const uint8_t* v) { febytes(v); febytes(v + 16); }
+    void path_tail(const PathH& q) {
+        u64(q.dirs.size());
+        for (size_t i = 0; i < q.dirs.size(); i++) { bytes(&q.digests[32 * i], 32); u32(q.dirs[i]); }
+    }
+    void query(const QueryH& q) {
+        u64(q.paths.size());
+        for (const PathH& ph : q.paths) { pair(ph.value.data()); path_tail(ph); }
+    }
+};
+void write_fri_proof(const ml_fri_proof* p, Writer& w) {
+    w.u64(p->commitments.size() / 32);
+    w.bytes(p->commitments.data(), p->commitments.size());
+    w.u64(p->queries.size());
+    for (const QueryH& q : p->queries) w.query(q);
+    uint8_t le[16];
+    hfe_store(le, p->last_elem);
+    w.febytes(le);
+    w.bytes(p->last_random, 32);
+}
+void write_bfri_proof(const ml_bfri_proof* p, Writer& w) {
+    w.bytes(p->batch_commitment, 32);
+    w.u64(p->commitments.size() / 32);
+    w.bytes(p->commitments.data(), p->commitments.size());
+    w.u64(p->queries.size());
+    for (const BQueryH& q : p->queries) {
+        const size_t nb = q.batch_path.value.size() / 32;
+        w.u64(nb);
+        for (size_t j = 0; j < nb; j++) w.pair(&q.batch_path.value[32 * j]);
+        w.path_tail(q.batch_path);
+        w.query(q.query);
+    }
+    uint8_t le[16];
+    hfe_store(le, p->last_elem);
+    w.febytes(le);
+    w.bytes(p->last_random, 32);
+}
+
+// ------------------------------------------------------------------ batched FRI prover data (batched_fri.rs:9-14)
+struct BatchedFri {
+    std::vector<fe*> codes;      // device, n elements each
+    bool owns_codes = true;
+    fe** codes_ptrs_dev = nullptr;
+    size_t n = 0;
+    ml_merkle* batch_layer = nullptr;
+    hfe fingerprint_r = 0;
+    ml_fri* fri = nullptr;
+    ~BatchedFri() {
+        if (owns_codes)
+            for (fe* c : codes) cudaFree(c);
+        if (codes_ptrs_dev) cudaFree(codes_ptrs_dev);
+        if (batch_layer) { batch_layer->owns_data = false; free_merkle(batch_layer); }
+        free_fri(fri);
+    }
+};
+// BatchedFriProverData::init (batched_fri.rs:41-99)
+int bfri_init(BatchedFri* b, ml_transcript* t, cudaStream_t s) {
+    const size_t B = b->codes.size(), n = b->n;
+    if (B == 0) { set_error("Codes must not be empty"); return ML_ERR_SIZE; }
+    MLB_TRY(check_code_len(n));
+    MLB_CUDA(cudaMalloc((void**)&b->codes_ptrs_dev, B * sizeof(fe*)));
+    MLB_TRY(h2d(b->codes_ptrs_dev, b->codes.data(), B * sizeof(fe*), s));
+    MLB_TRY(new_merkle(n / 2, &b->batch_layer));
+    b->batch_layer->kind = ml_merkle::RS_CODE;
+    b->batch_layer->item_bytes = 32;
+    b->batch_layer->n_batches = B;
+    for (fe* c : b->codes) b->batch_layer->data.push_back(c);
+    b->batch_layer->owns_data = false;
+    MLB_TRY(merkle_batched_rs_launch(b->codes_ptrs_dev, B, n, b->batch_layer->digests, s));  // :77
+    MLB_TRY(merkle_fetch_root(b->batch_layer, s));
+    t->sha.update(b->batch_layer->root, 32);  // :80
+    b->fingerprint_r = challenge(t);          // :83
+    absorb_fe(t, b->fingerprint_r);           // :86
+    b->fri = new ml_fri();                    // :89-92
+    b->fri->log_n0 = (int)ilog2(n);
+    return ML_OK;
+}
+// batched_fold_step (batched_fri.rs:101-181)
+int bfri_batched_fold_step(Ctx* ctx, BatchedFri* b, hfe r, ml_transcript* t, cudaStream_t s) {
+    const size_t n = b->n;
+    if (n <= ((size_t)1 << ML_LOG_BLOWUP)) return ML_OK;
+    const size_t half_n = n >> 1;
+    fe* next;
+    MLB_CUDA(cudaMalloc((void**)&next, half_n * 16));
+    int st = fri_batched_fold_launch(ctx, b->codes_ptrs_dev, b->codes.size(), n, next, b->fingerprint_r, r, b->fri->log_n0, s);
+    if (st != ML_OK) { cudaFree(next); return st; }
+    return fold_finish(b->fri, next, half_n, t, s);
+}
+// query phase of BatchedFriProof::prove / BatchedPCSProof::prove (batched_fri.rs:207-225, 296-308)
+int bfri_assemble(BatchedFri* b, ml_transcript* t, ml_bfri_proof* p, cudaStream_t s) {
+    const size_t n = b->n, L = n / 2, B = b->codes.size();
+    if (b->fri->layers.empty()) { set_error("open_query_at: no folded layer (domain too small)"); return ML_ERR_OUT_OF_RANGE; }
+    std::vector<size_t> idx;
+    derive_indices(t, n, idx);
+    const size_t nq = idx.size();
+    // batch layer: values of all codes + path in the batch tree
+    std::vector<PathJob> jobs(nq);
+    const int depth = (int)ilog2(L);
+    for (size_t q = 0; q < nq; q++) {
+        jobs[q].digests = b->batch_layer->digests; jobs[q].code = nullptr; jobs[q].n_leaves = L; jobs[q].index = idx[q];
+        jobs[q].depth = depth; jobs[q].dig_off = q * 32ull * depth; jobs[q].val_off = 0;
+    }
+    std::vector<unsigned long long> idx64(idx.begin(), idx.end());
+    Scratch djobs(s), dpaths(s), didx(s), dvals(s);
+    MLB_TRY(djobs.alloc(nq * sizeof(PathJob)));
+    MLB_TRY(dpaths.alloc(nq * 32 * (size_t)(depth ? depth : 1)));
+    MLB_TRY(didx.alloc(nq * 8));
+    MLB_TRY(dvals.alloc(nq * B * 32));
+    MLB_TRY(h2d(djobs.p, jobs.data(), nq * sizeof(PathJob), s));
+    MLB_TRY(h2d(didx.p, idx64.data(), nq * 8, s));
+    gather_paths_kernel<<<(unsigned)nq, 64, 0, s>>>(djobs.as<PathJob>(), dpaths.as<uint8_t>());
+    MLB_KERNEL_CHECK();
+    gather_batch_values_kernel<<<(unsigned)nq, 64, 0, s>>>(b->codes_ptrs_dev, (int)B, L, didx.as<unsigned long long>(), dvals.as<uint8_t>());
+    MLB_KERNEL_CHECK();
+    std::vector<uint8_t> hp(nq * 32 * (size_t)depth), hv(nq * B * 32);
+    MLB_TRY(d2h_sync(hp.data(), dpaths.p, hp.size(), s));
+    MLB_TRY(d2h_sync(hv.data(), dvals.p, hv.size(), s));
+    std::vector<size_t> sub(nq);
+    for (size_t q = 0; q < nq; q++) sub[q] = idx[q] % (L / 2);  // :217-218
+    std::vector<QueryH> qs;
+    MLB_TRY(fri_open_queries(b->fri, sub, qs, s));
+    p->queries.resize(nq);
+    for (size_t q = 0; q < nq; q++) {
+        PathH& bp = p->queries[q].batch_path;
+        bp.value.assign(hv.begin() + q * B * 32, hv.begin() + (q + 1) * B * 32);
+        bp.digests.assign(hp.begin() + q * 32 * (size_t)depth, hp.begin() + (q + 1) * 32 * (size_t)depth);
+        fill_dirs(bp, idx[q], depth);
+        p->queries[q].query = std::move(qs[q]);
+    }
+    memcpy(p->batch_commitment, b->batch_layer->root, 32);
+    p->commitments.resize(32 * b->fri->layers.size());
+    for (size_t j = 0; j < b->fri->layers.size(); j++) memcpy(&p->commitments[32 * j], b->fri->layers[j].tree->root, 32);
+    p->last_elem = b->fri->last;
+    t->sha.digest(p->last_random);
+    return ML_OK;
+}
+int bquery_verify(const BQueryH& bq, const ml_bfri_proof* fp, size_t n, size_t index, hfe gen, const hfe* rs, hfe fr) {  // batched_fri.rs:228-282
+    const size_t nc = fp->commitments.size() / 32;
+    if (bq.query.paths.size() != nc) return ML_V_WRONG_NUM_PATHS;
+    int st = path_verify(bq.batch_path, fp->batch_commitment, index);
+    if (st != ML_V_OK) return st;
+    const size_t nb = bq.batch_path.value.size() / 32;
+    hfe value = 0, minus_value = 0, two = 2;
+    for (size_t j = 0; j < nb; j++) {
+        value = hfe_add(hfe_mul(value, fr), hfe_load(&bq.batch_path.value[32 * j]));
+        minus_value = hfe_add(hfe_mul(minus_value, fr), hfe_load(&bq.batch_path.value[32 * j + 16]));
+    }
+    hfe gp = hfe_pow(gen, (hfe)index);
+    hfe even = hfe_div(hfe_add(value, minus_value), two);
+    hfe odd = hfe_div(hfe_sub(value, minus_value), hfe_mul(two, gp));
+    hfe expect = hfe_add(even, hfe_mul(rs[0], odd));
+    if (bq.query.paths.empty()) return fp->last_elem == expect ? ML_V_OK : ML_V_QUERY_MISMATCH;
+    const size_t next_n = n / 2, next_index = index % next_n;
+    const PathH& np = bq.query.paths[0];
+    hfe next_value = next_index == index ? hfe_load(np.value.data()) : hfe_load(np.value.data() + 16);
+    if (next_value != expect) return ML_V_QUERY_MISMATCH;
+    return query_verify(bq.query, fp->commitments.data(), nc, fp->last_elem, next_n, next_index, hfe_mul(gen, gen), rs + 1);
+}
+int bfri_verify_queries(const ml_bfri_proof* p, ml_transcript* t, const hfe* rs, hfe fr) {  // batched_fri.rs:356-397
+    if (p->queries.size() != ML_NUM_QUERIES) return ML_V_WRONG_NUM_QUERIES;
+    const size_t nc = p->commitments.size() / 32;
+    const size_t log_domain = nc + 1 + ML_LOG_BLOWUP, domain = (size_t)1 << log_domain;
+    hfe gen;
+    if (!hfe_pow2_generator(log_domain, &gen)) return ML_V_QUERY_MISMATCH;
+    for (const BQueryH& q : p->queries) {
+        size_t idx = next_query_index(t, domain);
+        int st = bquery_verify(q, p, domain / 2, idx, gen, rs, fr);
+        if (st != ML_V_OK) return st;
+        absorb_index(t, idx);
+    }
+    uint8_t lr[32];
+    t->sha.digest(lr);
+    return memcmp(lr, p->last_random, 32) == 0 ? ML_V_OK : ML_V_LAST_RANDOM;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ================================================================== Merkle
+int ml_merkle_commit(const uint8_t* data, size_t item_bytes, size_t n_items, ml_merkle** out) {
+    const uint8_t* one[1] = {data};
+    int st = ml_merkle_batch_commit(one, 1, item_bytes, n_items, out);
+    if (st == ML_OK) (*out)->n_batches = 0;
+    return st;
+}
+int ml_merkle_batch_commit(const uint8_t* const* data, size_t n_batches, size_t item_bytes, size_t n_items, ml_merkle** out) {
+    API_BEGIN
+    if (n_batches == 0) { set_error("Data must not be empty"); return ML_ERR_SIZE; }
+    if (!is_pow2(n_items)) { set_error("Data length must be a power of two"); return ML_ERR_NOT_POW2; }
+    cudaStream_t s = ctx->stream;
+    ml_merkle* m;
+    MLB_TRY(new_merkle(n_items, &m));
+    m->kind = ml_merkle::BYTES;
+    m->item_bytes = item_bytes;
+    m->n_batches = n_batches;
+    int st = ML_OK;
+    for (size_t b = 0; b < n_batches && st == ML_OK; b++) {
+        void* d = nullptr;
+        if (cudaMalloc(&d, n_items * item_bytes + 16) != cudaSuccess) { set_error("data allocation failed"); st = ML_ERR_ALLOC; break; }
+        m->data.push_back(d);
+        st = h2d(d, data[b], n_items * item_bytes, s);
+    }
+    if (st == ML_OK) st = merkle_set_ptrs(m, s);
+    if (st == ML_OK) st = merkle_bytes_launch((const uint8_t* const*)m->data_ptrs_dev, n_batches, item_bytes, n_items, m->digests, s);
+    if (st == ML_OK) st = merkle_fetch_root(m, s);
+    if (st != ML_OK) { free_merkle(m); return st; }
+    *out = m;
+    return ML_OK;
+}
+int ml_merkle_commit_rs_code_dev(const void* code_dev, size_t n, void* stream, ml_merkle** out) {
+    API_BEGIN
+    (void)ctx;
+    MLB_TRY(check_code_len(n));
+    cudaStream_t s = ST(stream);
+    ml_merkle* m;
+    MLB_TRY(new_merkle(n / 2, &m));
+    m->kind = ml_merkle::RS_CODE;
+    m->item_bytes = 32;
+    m->data.push_back((void*)code_dev);
+    m->owns_data = false;
+    int st = merkle_rs_launch((const fe*)code_dev, n, m->digests, s);
+    if (st == ML_OK) st = merkle_fetch_root(m, s);
+    if (st != ML_OK) { free_merkle(m); return st; }
+    *out = m;
+    return ML_OK;
+}
+void ml_merkle_free(ml_merkle* m) { free_merkle(m); }
+int ml_merkle_root(const ml_merkle* m, uint8_t out[32]) { memcpy(out, m->root, 32); return ML_OK; }
+size_t ml_merkle_num_layers(const ml_merkle* m) { return ilog2(m->n_leaves) + 1; }
+size_t ml_merkle_layer_len(const ml_merkle* m, size_t layer) { return m->n_leaves >> layer; }
+int ml_merkle_layer(const ml_merkle* m, size_t layer, uint8_t* out) {
+    API_BEGIN
+    if (layer > ilog2(m->n_leaves)) return ML_ERR_OUT_OF_RANGE;
+    return d2h_sync(out, m->digests + 32 * merkle_layer_offset(m->n_leaves, layer), (m->n_leaves >> layer) * 32, ctx->stream);
+}
+int ml_merkle_open(const ml_merkle* m, size_t index, uint8_t* value, uint8_t* digests, uint8_t* dirs, size_t* path_len) {
+    API_BEGIN
+    if (index >= m->n_leaves) { set_error("open(%zu): None", index); return ML_ERR_OUT_OF_RANGE; }
+    cudaStream_t s = ctx->stream;
+    const int depth = (int)ilog2(m->n_leaves);
+    const size_t nb = m->n_batches ? m->n_batches : 1;
+    const size_t vbytes = nb * m->item_bytes;
+    Scratch dj(s), dout(s);
+    MLB_TRY(dj.alloc(sizeof(PathJob)));
+    MLB_TRY(dout.alloc(32 * (size_t)(depth + 1) + vbytes + 32));
+    PathJob pj;
+    pj.digests = m->digests; pj.code = nullptr; pj.n_leaves = m->n_leaves; pj.index = index; pj.depth = depth; pj.dig_off = 0; pj.val_off = 0;
+    MLB_TRY(h2d(dj.p, &pj, sizeof pj, s));
+    gather_paths_kernel<<<1, 64, 0, s>>>(dj.as<PathJob>(), dout.as<uint8_t>());
+    MLB_KERNEL_CHECK();
+    uint8_t* dval = dout.as<uint8_t>() + 32 * (size_t)(depth + 1);
+    if (m->kind == ml_merkle::BYTES) {
+        gather_bytes_kernel<<<1, 128, 0, s>>>((const uint8_t* const*)m->data_ptrs_dev, (int)nb, m->item_bytes, index, dval);
+        MLB_KERNEL_CHECK();
+    } else {
+        for (size_t b = 0; b < nb; b++) {
+            const fe* c = (const fe*)m->data[b];
+            MLB_CUDA(cudaMemcpyAsync(dval + 32 * b, c + index, 16, cudaMemcpyDeviceToDevice, s));
+            MLB_CUDA(cudaMemcpyAsync(dval + 32 * b + 16, c + index + m->n_leaves, 16, cudaMemcpyDeviceToDevice, s));
+        }
+    }
+    std::vector<uint8_t> host(32 * (size_t)(depth + 1) + vbytes);
+    MLB_TRY(d2h_sync(host.data(), dout.p, host.size(), s));
+    memcpy(digests, host.data(), 32 * (size_t)depth);
+    memcpy(value, host.data() + 32 * (size_t)(depth + 1), vbytes);
+    for (int l = 0; l < depth; l++) dirs[l] = ((index >> l) & 1) ? 0 : 1;
+    *path_len = (size_t)depth;
+    return ML_OK;
+}
+int ml_merkle_path_verify(const uint8_t* value, size_t value_bytes, const uint8_t* digests, const uint8_t* dirs, size_t path_len,
+                          const uint8_t root[32], size_t index) {
+    PathH p;
+    p.value.assign(value, value + value_bytes);
+    p.digests.assign(digests, digests + 32 * path_len);
+    p.dirs.assign(dirs, dirs + path_len);
+    return path_verify(p, root, index);
+}
+
+// ================================================================== FRI
+int ml_fri_init_dev(const void* code_dev, size_t n, ml_transcript* t, void* stream, ml_fri** out) {
+    API_BEGIN
+    (void)ctx;
+    MLB_TRY(check_code_len(n));
+    cudaStream_t s = ST(stream);
+    fe* code;
+    MLB_CUDA(cudaMalloc((void**)&code, n * 16));
+    MLB_CUDA(cudaMemcpyAsync(code, code_dev, n * 16, cudaMemcpyDeviceToDevice, s));
+    return fri_init_owned(out, code, n, true, t, s);
+}
+int ml_fri_init(const uint8_t* code_host, size_t n, ml_transcript* t, ml_fri** out) {
+    API_BEGIN
+    MLB_TRY(check_code_len(n));
+    cudaStream_t s = ctx->stream;
+    fe* code;
+    MLB_CUDA(cudaMalloc((void**)&code, n * 16));
+    MLB_CUDA(cudaMemcpyAsync(code, code_host, n * 16, cudaMemcpyHostToDevice, s));
+    return fri_init_owned(out, code, n, true, t, s);
+}
+static int check_gen_pows(const ml_fri* f, const uint8_t* gen_pows, size_t gen_pows_len) {
+    if (!gen_pows) return ML_OK;
+    if (gen_pows_len != ((size_t)1 << f->log_n0)) { set_error("gen_pows.len() must equal the domain size"); return ML_ERR_SIZE; }
+    hfe w;
+    hfe_pow2_generator((uint64_t)f->log_n0, &w);
+    if (gen_pows_len > 1 && hfe_load(gen_pows + 16) != w) { set_error("gen_pows[1] is not pow_2_generator(log2 domain)"); return ML_ERR_GENERATOR; }
+    return ML_OK;
+}
+int ml_fri_fold_step(ml_fri* f, const uint8_t* gen_pows, size_t gen_pows_len, size_t k, const uint8_t r[16], ml_transcript* t) {
+    API_BEGIN
+    MLB_TRY(check_gen_pows(f, gen_pows, gen_pows_len));
+    return fri_fold_step_impl(ctx, f, k, hfe_load(r), t, ctx->stream);
+}
+int ml_fri_fold_dev(const void* code_dev, size_t n, ml_transcript* t, void* stream, ml_fri** out) {
+    API_BEGIN
+    ml_fri* f;
+    MLB_TRY(ml_fri_init_dev(code_dev, n, t, stream, &f));
+    int st = fri_fold_all(ctx, f, t, ST(stream));
+    if (st != ML_OK) { free_fri(f); return st; }
+    *out = f;
+    return ML_OK;
+}
+int ml_fri_fold(const uint8_t* gen_pows, size_t gen_pows_len, const uint8_t* code, size_t n, ml_transcript* t, ml_fri** out) {
+    API_BEGIN
+    ml_fri* f;
+    MLB_TRY(ml_fri_init(code, n, t, &f));
+    int st = check_gen_pows(f, gen_pows, gen_pows_len);
+    if (st == ML_OK) st = fri_fold_all(ctx, f, t, ctx->stream);
+    if (st != ML_OK) { free_fri(f); return st; }
+    *out = f;
+    return ML_OK;
+}
+void ml_fri_free(ml_fri* f) { free_fri(f); }
+size_t ml_fri_num_trees(const ml_fri* f) { return f->layers.size(); }
+int ml_fri_tree(const ml_fri* f, size_t i, const ml_merkle** tree) {
+    if (i >= f->layers.size()) return ML_ERR_OUT_OF_RANGE;
+    *tree = f->layers[i].tree;
+    return ML_OK;
+}
+__global__ void pairs_kernel(const fe* __restrict__ code, size_t half, uint4* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < half; i += stride) {
+        out[2 * i] = *reinterpret_cast<const uint4*>(code + i);
+        out[2 * i + 1] = *reinterpret_cast<const uint4*>(code + i + half);
+    }
+}
+int ml_fri_tree_data(const ml_fri* f, size_t i, uint8_t* pairs_out) {
+    API_BEGIN
+    if (i >= f->layers.size()) return ML_ERR_OUT_OF_RANGE;
+    cudaStream_t s = ctx->stream;
+    const ml_fri::Layer& L = f->layers[i];
+    Scratch d(s);
+    MLB_TRY(d.alloc(L.n * 16));
+    size_t blocks = (L.n / 2 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pairs_kernel<<<(unsigned)blocks, 256, 0, s>>>(L.code, L.n / 2, d.as<uint4>());
+    MLB_KERNEL_CHECK();
+    return d2h_sync(pairs_out, d.p, L.n * 16, s);
+}
+int ml_fri_fold_roots(const ml_fri* f, uint8_t* out) {
+    for (size_t j = 0; j < f->layers.size(); j++) memcpy(out + 32 * j, f->layers[j].tree->root, 32);
+    return ML_OK;
+}
+int ml_fri_last_element(const ml_fri* f, uint8_t out[16], int* is_some) {
+    *is_some = f->has_last ? 1 : 0;
+    if (f->has_last) hfe_store(out, f->last);
+    return ML_OK;
+}
+int ml_fri_open_query_at(const ml_fri* f, size_t index, uint8_t* values, uint8_t* digests, uint8_t* dirs, size_t* path_lens) {
+    API_BEGIN
+    if (f->layers.empty() || index >= f->layers[0].n / 2) { set_error("open_query_at: index out of range"); return ML_ERR_OUT_OF_RANGE; }
+    std::vector<size_t> idx(1, index);
+    std::vector<QueryH> q;
+    MLB_TRY(fri_open_queries(f, idx, q, ctx->stream));
+    size_t doff = 0;
+    for (size_t j = 0; j < q[0].paths.size(); j++) {
+        const PathH& p = q[0].paths[j];
+        memcpy(values + 32 * j, p.value.data(), 32);
+        memcpy(digests + 32 * doff, p.digests.data(), p.digests.size());
+        memcpy(dirs + doff, p.dirs.data(), p.dirs.size());
+        path_lens[j] = p.dirs.size();
+        doff += p.dirs.size();
+    }
+    return ML_OK;
+}
+static int fri_prove_from(Ctx* ctx, ml_fri* f, size_t n, ml_transcript* t, cudaStream_t s, ml_fri_proof** out) {
+    int st = fri_fold_all(ctx, f, t, s);
+    ml_fri_proof* p = nullptr;
+    if (st == ML_OK) {
+        p = new ml_fri_proof();
+        st = assemble_fri_proof(f, n, t, p, s);
+    }
+    free_fri(f);
+    if (st != ML_OK) { delete p; return st; }
+    *out = p;
+    return ML_OK;
+}
+int ml_fri_prove_dev(const void* code_dev, size_t n, ml_transcript* t, void* stream, ml_fri_proof** out) {
+    API_BEGIN
+    ml_fri* f;
+    MLB_TRY(ml_fri_init_dev(code_dev, n, t, stream, &f));
+    return fri_prove_from(ctx, f, n, t, ST(stream), out);
+}
+int ml_fri_prove(const uint8_t* code, size_t n, const uint8_t* gen_pows, size_t gen_pows_len, ml_transcript* t, ml_fri_proof** out) {
+    API_BEGIN
+    ml_fri* f;
+    MLB_TRY(ml_fri_init(code, n, t, &f));
+    int st = check_gen_pows(f, gen_pows, gen_pows_len);
+    if (st != ML_OK) { free_fri(f); return st; }
+    return fri_prove_from(ctx, f, n, t, ctx->stream, out);
+}
+static int rs_encode_owned(Ctx* ctx, const void* coeffs_dev, size_t n, fe** code_out, cudaStream_t s) {
+    const size_t N = n << ML_LOG_BLOWUP;
+    MLB_TRY(check_code_len(N));
+    fe* code;
+    MLB_CUDA(cudaMalloc((void**)&code, N * 16));
+    int st = ntt_launch(ctx, (const fe*)coeffs_dev, code, (int)ilog2(N), false, true, s);
+    if (st != ML_OK) { cudaFree(code); return st; }
+    *code_out = code;
+    return ML_OK;
+}
+int ml_rs_fri_fold_dev(const void* coeffs_dev, size_t n, ml_transcript* t, void* stream, ml_fri** out) {
+    API_BEGIN
+    cudaStream_t s = ST(stream);
+    fe* code;
+    MLB_TRY(rs_encode_owned(ctx, coeffs_dev, n, &code, s));
+    ml_fri* f;
+    MLB_TRY(fri_init_owned(&f, code, n << ML_LOG_BLOWUP, true, t, s));
+    int st = fri_fold_all(ctx, f, t, s);
+    if (st != ML_OK) { free_fri(f); return st; }
+    *out = f;
+    return ML_OK;
+}
+int ml_rs_fri_prove_dev(const void* coeffs_dev, size_t n, ml_transcript* t, void* stream, ml_fri_proof** out) {
+    API_BEGIN
+    cudaStream_t s = ST(stream);
+    fe* code;
+    MLB_TRY(rs_encode_owned(ctx, coeffs_dev, n, &code, s));
+    ml_fri* f;
+    MLB_TRY(fri_init_owned(&f, code, n << ML_LOG_BLOWUP, true, t, s));
+    return fri_prove_from(ctx, f, n << ML_LOG_BLOWUP, t, s, out);
+}
+int ml_rs_fri_prove(const uint8_t* coeffs, size_t n, ml_transcript* t, ml_fri_proof** out) {
+    API_BEGIN
+    cudaStream_t s = ctx->stream;
+    Scratch d(s);
+    MLB_TRY(d.alloc(n * 16));
+    MLB_TRY(h2d(d.p, coeffs, n * 16, s));
+    return ml_rs_fri_prove_dev(d.p, n, t, s, out);
+}
+int ml_fri_verify(const ml_fri_proof* p) {  // fri/mod.rs:287-309
+    if (p->queries.size() != ML_NUM_QUERIES) return ML_V_WRONG_NUM_QUERIES;
+    ml_transcript t;
+    const size_t nc = p->commitments.size() / 32;
+    std::vector<hfe> rs(nc + 1);
+    for (size_t i = 0; i < nc; i++) {
+        t.sha.update(&p->commitments[32 * i], 32);
+        rs[i] = challenge(&t);
+    }
+    absorb_fe(&t, p->last_elem);
+    return fri_verify_queries(p, &t, rs.data());
+}
+void ml_fri_proof_free(ml_fri_proof* p) { delete p; }
+size_t ml_fri_proof_num_commitments(const ml_fri_proof* p) { return p->commitments.size() / 32; }
+int ml_fri_proof_commitments(const ml_fri_proof* p, uint8_t* out) { memcpy(out, p->commitments.data(), p->commitments.size()); return ML_OK; }
+int ml_fri_proof_last(const ml_fri_proof* p, uint8_t last_elem[16], uint8_t last_random[32]) {
+    hfe_store(last_elem, p->last_elem);
+    memcpy(last_random, p->last_random, 32);
+    return ML_OK;
+}
+size_t ml_fri_proof_serialized_len(const ml_fri_proof* p) { Writer w(nullptr); write_fri_proof(p, w); return w.n; }
+int ml_fri_proof_serialize(const ml_fri_proof* p, uint8_t* out) { Writer w(out); write_fri_proof(p, w); return ML_OK; }
+
+// ================================================================== sumcheck
+int ml_sumcheck_build_tables_for_pcs(const uint8_t* inputs, size_t n_vars, const uint8_t* evals, size_t height, ml_sumcheck** out) {
+    API_BEGIN
+    return sumcheck_build(ctx, inputs, n_vars, evals, false, height, ctx->stream, out);
+}
+int ml_sumcheck_build_tables_for_pcs_dev(const uint8_t* inputs, size_t n_vars, const void* evals_dev, size_t height, void* stream,
+                                         ml_sumcheck** out) {
+    API_BEGIN
+    return sumcheck_build(ctx, inputs, n_vars, evals_dev, true, height, ST(stream), out);
+}
+void ml_sumcheck_free(ml_sumcheck* s) { free_sumcheck(s); }
+size_t ml_sumcheck_height(const ml_sumcheck* s) { return s->height; }
+int ml_sumcheck_tables(const ml_sumcheck* sc, uint8_t* matrix_out, uint8_t* delta_out) {
+    API_BEGIN
+    MLB_TRY(d2h_sync(matrix_out, sc->matrix, sc->height * 16, ctx->stream));
+    return d2h_sync(delta_out, sc->delta, sc->height * 16, ctx->stream);
+}
+int ml_sumcheck_partial_sum(const ml_sumcheck* sc, const uint8_t r[16], uint8_t out[16]) {
+    API_BEGIN
+    hfe o;
+    MLB_TRY(sumcheck_partial_sum_launch(ctx, sc->matrix, sc->delta, sc->height, hfe_load(r), &o, ctx->stream));
+    hfe_store(out, o);
+    return ML_OK;
+}
+int ml_sumcheck_fold(ml_sumcheck* sc, const uint8_t r[16]) {
+    API_BEGIN
+    MLB_TRY(sumcheck_fold_launch(sc->matrix, sc->delta, sc->height, hfe_load(r), ctx->stream));
+    sc->height >>= 1;
+    MLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ML_OK;
+}
+int ml_sumcheck_compute_polynomial(ml_sumcheck* sc, size_t total_degree, uint8_t previous_sum[16], ml_transcript* t,
+                                   uint8_t* nonzero_coeffs_out, uint8_t r_out[16]) {
+    API_BEGIN
+    if (total_degree > 16) { set_error("total_degree too large"); return ML_ERR_ARG; }
+    hfe prev = hfe_load(previous_sum), r;
+    std::vector<hfe> nz(total_degree ? total_degree : 1);
+    MLB_TRY(sumcheck_round(ctx, sc, total_degree, &prev, t, nz.data(), &r, ctx->stream));
+    for (size_t i = 0; i < total_degree; i++) hfe_store(nonzero_coeffs_out + 16 * i, nz[i]);
+    hfe_store(previous_sum, prev);
+    hfe_store(r_out, r);
+    return ML_OK;
+}
+int ml_sumcheck_compute_polynomials(ml_sumcheck* sc, size_t composition_degree, ml_transcript* t, const uint8_t sum[16],
+                                    uint8_t* coeffs_out, uint8_t* randoms_out) {
+    API_BEGIN
+    const size_t td = composition_degree + 1;  // :159
+    if (td > 16) { set_error("composition_degree too large"); return ML_ERR_ARG; }
+    hfe prev = hfe_load(sum);
+    const size_t rounds = sc->height ? ilog2(sc->height) : 0;  // :160
+    std::vector<hfe> nz(td);
+    for (size_t k = 0; k < rounds; k++) {
+        hfe r;
+        MLB_TRY(sumcheck_round(ctx, sc, td, &prev, t, nz.data(), &r, ctx->stream));
+        for (size_t i = 0; i < td; i++) hfe_store(coeffs_out + 16 * (k * td + i), nz[i]);
+        hfe_store(randoms_out + 16 * k, r);
+    }
+    MLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ML_OK;
+}
+int ml_delta_evaluate(const uint8_t* data, const uint8_t* points, size_t n, uint8_t out[16]) {
+    std::vector<hfe> a(n), b(n);
+    for (size_t i = 0; i < n; i++) { a[i] = hfe_load(data + 16 * i); b[i] = hfe_load(points + 16 * i); }
+    hfe_store(out, delta_evaluate(a.data(), b.data(), n));
+    return ML_OK;
+}
+
+// ================================================================== multilinear PCS
+int ml_pcs_prove_dev(const uint8_t* inputs, size_t n_vars, const uint8_t output[16], const void* evals_dev, size_t n, ml_transcript* t,
+                     void* stream, ml_pcs_proof** out) {
+    API_BEGIN
+    cudaStream_t s = ST(stream);
+    if (!is_pow2(n) || n < 2 || n_vars >= 40 || ((size_t)1 << n_vars) != n) { set_error("PCSProof::prove: need 2^n_vars == evals.len() >= 2"); return ML_ERR_SIZE; }
+    const size_t domain = n << ML_LOG_BLOWUP;  // :97
+    fe* code;
+    MLB_TRY(encode_poly(ctx, (const fe*)evals_dev, n, &code, s));  // :101-107
+    // PCSProverData::fold (:43-76)
+    ml_fri* f;
+    MLB_TRY(fri_init_owned(&f, code, domain, true, t, s));  // :30
+    ml_sumcheck* sc = nullptr;
+    int st = sumcheck_build(ctx, inputs, n_vars, evals_dev, true, n, s, &sc);  // :31
+    ml_pcs_proof* p = new ml_pcs_proof();
+    const size_t num_steps = ilog2(domain) - ML_LOG_BLOWUP;  // :52
+    p->sumcheck.resize(2 * num_steps);
+    hfe prev = hfe_load(output);
+    for (size_t k = 0; k < num_steps && st == ML_OK; k++) {
+        hfe r;
+        st = sumcheck_round(ctx, sc, 2, &prev, t, &p->sumcheck[2 * k], &r, s);  // :61-66
+        if (st == ML_OK) st = fri_fold_step_impl(ctx, f, k, r, t, s);           // :72
+    }
+    if (st == ML_OK && !f->has_last) { set_error("last_element is None"); st = ML_ERR_SIZE; }
+    if (st == ML_OK) st = assemble_fri_proof(f, domain, t, &p->fri, s);  // :113-129
+    if (st == ML_OK) {
+        p->inputs.resize(n_vars);
+        for (size_t i = 0; i < n_vars; i++) p->inputs[i] = hfe_load(inputs + 16 * i);
+        p->output = hfe_load(output);
+    }
+    free_fri(f);
+    free_sumcheck(sc);
+    if (st != ML_OK) { delete p; return st; }
+    *out = p;
+    return ML_OK;
+}
+int ml_pcs_prove(const uint8_t* inputs, size_t n_vars, const uint8_t output[16], const uint8_t* evals, size_t n, ml_transcript* t,
+                 ml_pcs_proof** out) {
+    API_BEGIN
+    cudaStream_t s = ctx->stream;
+    Scratch d(s);
+    MLB_TRY(d.alloc(n * 16));
+    MLB_TRY(h2d(d.p, evals, n * 16, s));
+    return ml_pcs_prove_dev(inputs, n_vars, output, d.p, n, t, s, out);
+}
+int ml_pcs_verify(const ml_pcs_proof* p, ml_transcript* t) {  // multilinear_pcs.rs:138-190
+    const ml_fri_proof* fp = &p->fri;
+    if (fp->queries.size() != ML_NUM_QUERIES) return ML_V_WRONG_NUM_QUERIES;
+    const size_t n = fp->commitments.size() / 32;
+    if (n == 0 || 2 * n != p->sumcheck.size() || n != p->inputs.size()) { set_error("assert_eq!(n, ...) failed"); return ML_ERR_SIZE; }
+    std::vector<hfe> rs(n);
+    for (size_t i = 0; i < n; i++) {
+        t->sha.update(&fp->commitments[32 * i], 32);
+        absorb_fe(t, p->sumcheck[2 * i]);
+        absorb_fe(t, p->sumcheck[2 * i + 1]);
+        rs[i] = challenge(t);
+    }
+    absorb_fe(t, fp->last_elem);
+    int st = sumcheck_replay(p->sumcheck, p->output, p->inputs, rs, fp->last_elem);
+    if (st != ML_V_OK) return st;
+    return fri_verify_queries(fp, t, rs.data());
+}
+void ml_pcs_proof_free(ml_pcs_proof* p) { delete p; }
+const ml_fri_proof* ml_pcs_proof_fri(const ml_pcs_proof* p) { return &p->fri; }
+size_t ml_pcs_proof_num_rounds(const ml_pcs_proof* p) { return p->sumcheck.size() / 2; }
+int ml_pcs_proof_sumcheck_coeffs(const ml_pcs_proof* p, uint8_t* out) {
+    for (size_t i = 0; i < p->sumcheck.size(); i++) hfe_store(out + 16 * i, p->sumcheck[i]);
+    return ML_OK;
+}
+
+// ================================================================== batched FRI / PCS
+int ml_fingerprint(const uint8_t r[16], const uint8_t* coeffs, size_t n, uint8_t out[16]) {
+    std::vector<hfe> c(n);
+    for (size_t i = 0; i < n; i++) c[i] = hfe_load(coeffs + 16 * i);
+    hfe_store(out, fingerprint_host(hfe_load(r), c.data(), n));
+    return ML_OK;
+}
+int ml_batched_fri_prove(const uint8_t* const* codes, size_t n_codes, size_t n, const uint8_t* gen_pows, size_t gen_pows_len,
+                         ml_transcript* t, ml_bfri_proof** out) {
+    API_BEGIN
+    cudaStream_t s = ctx->stream;
+    if (n_codes == 0) { set_error("Codes must not be empty"); return ML_ERR_SIZE; }
+    MLB_TRY(check_code_len(n));
+    if (gen_pows && gen_pows_len != n) { set_error("gen_pows.len() must equal the domain size"); return ML_ERR_SIZE; }
+    BatchedFri b;
+    b.n = n;
+    for (size_t j = 0; j < n_codes; j++) {
+        fe* c;
+        MLB_CUDA(cudaMalloc((void**)&c, n * 16));
+        b.codes.push_back(c);
+        MLB_TRY(h2d(c, codes[j], n * 16, s));
+    }
+    MLB_TRY(bfri_init(&b, t, s));
+    const size_t num_steps = ilog2(n) - ML_LOG_BLOWUP;  // batched_fri.rs:191
+    hfe r = challenge(t);                               // :194
+    MLB_TRY(bfri_batched_fold_step(ctx, &b, r, t, s));
+    for (size_t k = 1; k < num_steps; k++) {            // :198-201
+        r = challenge(t);
+        MLB_TRY(fri_fold_step_impl(ctx, b.fri, k, r, t, s));
+    }
+    if (!b.fri->has_last) { set_error("last_element is None"); return ML_ERR_SIZE; }
+    ml_bfri_proof* p = new ml_bfri_proof();
+    int st = bfri_assemble(&b, t, p, s);
+    if (st != ML_OK) { delete p; return st; }
+    *out = p;
+    return ML_OK;
+}
+int ml_batched_fri_verify(const ml_bfri_proof* p) {  // batched_fri.rs:320-354
+    ml_transcript t;
+    t.sha.update(p->batch_commitment, 32);
+    hfe fr = challenge(&t);
+    absorb_fe(&t, fr);
+    const size_t nc = p->commitments.size() / 32;
+    std::vector<hfe> rs(nc + 1);
+    rs[0] = challenge(&t);
+    for (size_t i = 0; i < nc; i++) {
+        t.sha.update(&p->commitments[32 * i], 32);
+        rs[i + 1] = challenge(&t);
+    }
+    absorb_fe(&t, p->last_elem);
+    return bfri_verify_queries(p, &t, rs.data(), fr);
+}
+void ml_bfri_proof_free(ml_bfri_proof* p) { delete p; }
+int ml_bfri_proof_batch_commitment(const ml_bfri_proof* p, uint8_t out[32]) { memcpy(out, p->batch_commitment, 32); return ML_OK; }
+size_t ml_bfri_proof_num_commitments(const ml_bfri_proof* p) { return p->commitments.size() / 32; }
+int ml_bfri_proof_commitments(const ml_bfri_proof* p, uint8_t* out) { memcpy(out, p->commitments.data(), p->commitments.size()); return ML_OK; }
+int ml_bfri_proof_last(const ml_bfri_proof* p, uint8_t last_elem[16], uint8_t last_random[32]) {
+    hfe_store(last_elem, p->last_elem);
+    memcpy(last_random, p->last_random, 32);
+    return ML_OK;
+}
+size_t ml_bfri_proof_serialized_len(const ml_bfri_proof* p) { Writer w(nullptr); write_bfri_proof(p, w); return w.n; }
+int ml_bfri_proof_serialize(const ml_bfri_proof* p, uint8_t* out) { Writer w(out); write_bfri_proof(p, w); return ML_OK; }
+
+int ml_batched_pcs_prove_dev(const uint8_t* inputs, size_t n_vars, const uint8_t* outputs, size_t n_polys, const void* const* evals_dev,
+                             size_t n, ml_transcript* t, void* stream, ml_bpcs_proof** out) {
+    API_BEGIN
+    cudaStream_t s = ST(stream);
+    if (n_polys == 0 || !is_pow2(n) || n < 2 || n_vars >= 40 || ((size_t)1 << n_vars) != n) { set_error("BatchedPCSProof::prove: bad sizes"); return ML_ERR_SIZE; }
+    const size_t domain = n << ML_LOG_BLOWUP;  // batched_pcs.rs:136
+    BatchedFri b;
+    b.n = domain;
+    for (size_t j = 0; j < n_polys; j++) {  // :144-149
+        fe* code;
+        MLB_TRY(encode_poly(ctx, (const fe*)evals_dev[j], n, &code, s));
+        b.codes.push_back(code);
+    }
+    // BatchedPCSProverData::init (:37-77)
+    t->sha.update(inputs, n_vars * 16);    // :44-46
+    t->sha.update(outputs, n_polys * 16);  // :47-49
+    MLB_TRY(bfri_init(&b, t, s));
+    const hfe fr = b.fingerprint_r;
+    // fingerprinted evaluation table (:55-63) straight into the sumcheck matrix
+    ml_sumcheck* sc = new ml_sumcheck();
+    sc->height = n;
+    Scratch dptrs(s);
+    int st = ML_OK;
+    if (cudaMalloc((void**)&sc->matrix, n * 16) != cudaSuccess || cudaMalloc((void**)&sc->delta, n * 16) != cudaSuccess) { set_error("allocation failed"); st = ML_ERR_ALLOC; }
+    if (st == ML_OK) st = dptrs.alloc(n_polys * sizeof(void*));
+    if (st == ML_OK) st = h2d(dptrs.p, evals_dev, n_polys * sizeof(void*), s);
+    if (st == ML_OK) st = fingerprint_rows_launch((const fe* const*)dptrs.p, n_polys, n, fr, sc->matrix, s);
+    std::vector<hfe> pts(n_vars), outs(n_polys);
+    for (size_t i = 0; i < n_vars; i++) pts[i] = hfe_load(inputs + 16 * i);
+    for (size_t i = 0; i < n_polys; i++) outs[i] = hfe_load(outputs + 16 * i);
+    if (st == ML_OK) st = eq_table_launch(ctx, pts.data(), n_vars, sc->delta, s);  // :66-67
+    if (st == ML_OK && cudaStreamSynchronize(s) != cudaSuccess) st = ML_ERR_CUDA;
+    ml_bpcs_proof* p = new ml_bpcs_proof();
+    const size_t num_steps = ilog2(domain) - ML_LOG_BLOWUP;  // :90
+    p->sumcheck.resize(2 * num_steps);
+    hfe prev = fingerprint_host(fr, outs.data(), n_polys);   // :92-94
+    for (size_t k = 0; k < num_steps && st == ML_OK; k++) {  // :100-123
+        hfe r;
+        st = sumcheck_round(ctx, sc, 2, &prev, t, &p->sumcheck[2 * k], &r, s);
+        if (st != ML_OK) break;
+        st = k == 0 ? bfri_batched_fold_step(ctx, &b, r, t, s) : fri_fold_step_impl(ctx, b.fri, k, r, t, s);
+    }
+    if (st == ML_OK && !b.fri->has_last) { set_error("last_element is None"); st = ML_ERR_SIZE; }
+    if (st == ML_OK) st = bfri_assemble(&b, t, &p->fri, s);  // :155-173
+    free_sumcheck(sc);
+    if (st != ML_OK) { delete p; return st; }
+    p->inputs = pts;
+    p->outputs = outs;
+    *out = p;
+    return ML_OK;
+}
+int ml_batched_pcs_prove(const uint8_t* inputs, size_t n_vars, const uint8_t* outputs, size_t n_polys, const uint8_t* const* evals, size_t n,
+                         ml_transcript* t, ml_bpcs_proof** out) {
+    API_BEGIN
+    cudaStream_t s = ctx->stream;
+    std::vector<void*> dev(n_polys, nullptr);
+    int st = ML_OK;
+    for (size_t j = 0; j < n_polys && st == ML_OK; j++) {
+        if (cudaMalloc(&dev[j], n * 16 + 16) != cudaSuccess) { set_error("allocation failed"); st = ML_ERR_ALLOC; break; }
+        st = h2d(dev[j], evals[j], n * 16, s);
+    }
+    if (st == ML_OK) st = ml_batched_pcs_prove_dev(inputs, n_vars, outputs, n_polys, dev.data(), n, t, s, out);
+    cudaStreamSynchronize(s);
+    for (void* d : dev)
+        if (d) cudaFree(d);
+    return st;
+}
+int ml_batched_pcs_verify(const ml_bpcs_proof* p, ml_transcript* t) {  // batched_pcs.rs:182-253
+    const ml_bfri_proof* fp = &p->fri;
+    if (fp->queries.size() != ML_NUM_QUERIES) return ML_V_WRONG_NUM_QUERIES;
+    const size_t n = fp->commitments.size() / 32 + 1;
+    if (2 * n != p->sumcheck.size() || n != p->inputs.size()) { set_error("assert_eq!(n, ...) failed"); return ML_ERR_SIZE; }
+    std::vector<hfe> rs(n);
+    for (hfe x : p->inputs) absorb_fe(t, x);
+    for (hfe x : p->outputs) absorb_fe(t, x);
+    hfe fr = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (i == 0) {
+            t->sha.update(fp->batch_commitment, 32);
+            fr = challenge(t);
+            absorb_fe(t, fr);
+        } else t->sha.update(&fp->commitments[32 * (i - 1)], 32);
+        absorb_fe(t, p->sumcheck[2 * i]);
+        absorb_fe(t, p->sumcheck[2 * i + 1]);
+        rs[i] = challenge(t);
+    }
+    absorb_fe(t, fp->last_elem);
+    hfe sum = fingerprint_host(fr, p->outputs.data(), p->outputs.size());
+    int st = sumcheck_replay(p->sumcheck, sum, p->inputs, rs, fp->last_elem);
+    if (st != ML_V_OK) return st;
+    return bfri_verify_queries(fp, t, rs.data(), fr);
+}
+void ml_bpcs_proof_free(ml_bpcs_proof* p) { delete p; }
+const ml_bfri_proof* ml_bpcs_proof_fri(const ml_bpcs_proof* p) { return &p->fri; }
+size_t ml_bpcs_proof_num_rounds(const ml_bpcs_proof* p) { return p->sumcheck.size() / 2; }
+int ml_bpcs_proof_sumcheck_coeffs(const ml_bpcs_proof* p, uint8_t* out) {
+    for (size_t i = 0; i < p->sumcheck.size(); i++) hfe_store(out + 16 * i, p->sumcheck[i]);
+    return ML_OK;
+}
+
+// ================================================================== sharded batched commit (config 5)
+int ml_batched_leaf_subtree_dev(const void* const* pairs_dev, size_t n_codes, size_t leaf_count, void* stream, uint8_t root_out[32]) {
+    API_BEGIN
+    (void)ctx;
+    cudaStream_t s = ST(stream);
+    if (!is_pow2(leaf_count) || n_codes == 0) { set_error("leaf_count must be a power of two"); return ML_ERR_NOT_POW2; }
+    Scratch dig(s), ptrs(s);
+    MLB_TRY(dig.alloc(2 * leaf_count * 32));
+    MLB_TRY(ptrs.alloc(n_codes * sizeof(void*)));
+    MLB_TRY(h2d(ptrs.p, pairs_dev, n_codes * sizeof(void*), s));
+    MLB_TRY(merkle_batched_pairs_launch((const uint8_t* const*)ptrs.p, n_codes, leaf_count, dig.as<uint8_t>(), s));
+    const int top = (int)ilog2(leaf_count);
+    return d2h_sync(root_out, dig.as<uint8_t>() + 32 * merkle_layer_offset(leaf_count, top), 32, s);
+}
+int ml_merkle_top_from_roots(const uint8_t* roots, size_t n_roots, uint8_t root_out[32]) {
+    if (!is_pow2(n_roots)) { set_error("n_roots must be a power of two"); return ML_ERR_NOT_POW2; }
+    std::vector<uint8_t> cur(roots, roots + 32 * n_roots), nxt;
+    while (cur.size() > 32) {  // O(n_roots) host hashing of the subtree roots gathered over NCCL
+        nxt.resize(cur.size() / 2);
+        for (size_t i = 0; i < nxt.size() / 32; i++) hash_node_host(&cur[64 * i], &cur[64 * i + 32], &nxt[32 * i]);
+        cur.swap(nxt);
+    }
+    memcpy(root_out, cur.data(), 32);
+    return ML_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+// Sumcheck tables for the PCS (src/constraint_system/sumcheck.rs:127-277), width 1, composition |x| x[0]
+// (src/fri/multilinear_pcs.rs:56-57): per round the prover needs
+//     e1 = sum_i m[i+off] * d[i+off]                                  (partial_sum at r = 1, :208-218)
+//     e2 = sum_i (2 m[i+off] - m[i]) * (2 d[i+off] - d[i])            (partial_sum at r = 2, :219-231; s = 1 - r = -1)
+// then folds both tables x[i] <- (1-r) x[i] + r x[i+off] (:234-247), computed as x[i] + r (x[i+off] - x[i]).
+// Streaming kernels: each product is accumulated unreduced in a 288-bit register accumulator and reduced once
+// per thread; the block results are added mod M (integer-exact, order-independent).
+#include "field.cuh"
+#include "internal.h"
+#include "reduce.cuh"
+
+namespace mlb {
+
+static const int SC_THREADS = 256;
+static const int SC_MAX_BLOCKS = 148 * 4;
+
+// partials[2*blockIdx + {0,1}] = (e1, e2) of this CTA's slice
+__global__ void __launch_bounds__(SC_THREADS) sumcheck_sums_kernel(const fe* __restrict__ m, const fe* __restrict__ d, size_t off,
+                                                                   fe* __restrict__ partials) {
+    __shared__ fe scratch[32];
+    fe_acc a1, a2;
+    acc_zero(a1);
+    acc_zero(a2);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < off; i += stride) {
+        fe m0 = fe_load_nc(m + i), m1 = fe_load_nc(m + i + off), d0 = fe_load_nc(d + i), d1 = fe_load_nc(d + i + off);
+        acc_mul_add(a1, m1, d1);
+        fe mm = fe_sub(fe_add(m1, m1), m0), dd = fe_sub(fe_add(d1, d1), d0);
+        acc_mul_add(a2, mm, dd);
+    }
+    fe s1 = block_sum(acc_reduce(a1), scratch);
+    fe s2 = block_sum(acc_reduce(a2), scratch);
+    if (threadIdx.x == 0) {
+        fe_store(partials + 2 * blockIdx.x, s1);
+        fe_store(partials + 2 * blockIdx.x + 1, s2);
+    }
+}
+// general partial_sum(r): r == 1 -> sum m1*d1 ; else sum (s m0 + r m1)(s d0 + r d1), s = 1 - r
+__global__ void __launch_bounds__(SC_THREADS) sumcheck_partial_kernel(const fe* __restrict__ m, const fe* __restrict__ d, size_t off, fe r,
+                                                                      fe sm1, int is_one, fe* __restrict__ partials) {
+    __shared__ fe scratch[32];
+    fe_acc a;
+    acc_zero(a);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < off; i += stride) {
+        fe m1 = fe_load_nc(m + i + off), d1 = fe_load_nc(d + i + off);
+        if (is_one) acc_mul_add(a, m1, d1);
+        else {
+            fe m0 = fe_load_nc(m + i), d0 = fe_load_nc(d + i);
+            fe mm = fe_add(fe_mul(sm1, m0), fe_mul(r, m1)), dd = fe_add(fe_mul(sm1, d0), fe_mul(r, d1));
+            acc_mul_add(a, mm, dd);
+        }
+    }
+    fe s = block_sum(acc_reduce(a), scratch);
+    if (threadIdx.x == 0) fe_store(partials + blockIdx.x, s);
+}
+// out[c] = sum_b partials[b*ncols + c]
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const fe* __restrict__ partials, int count, int ncols, fe* __restrict__ out) {
+    __shared__ fe scratch[32];
+    for (int c = 0; c < ncols; c++) {
+        fe a = fe_zero();
+        for (int b = threadIdx.x; b < count; b += blockDim.x) a = fe_add(a, partials[(size_t)b * ncols + c]);
+        a = block_sum(a, scratch);
+        if (threadIdx.x == 0) fe_store(out + c, a);
+    }
+}
+__global__ void __launch_bounds__(256) sumcheck_fold_kernel(fe* __restrict__ m, fe* __restrict__ d, size_t off, fe r) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < off; i += stride) {
+        fe m0 = fe_load(m + i), m1 = fe_load(m + i + off), d0 = fe_load(d + i), d1 = fe_load(d + i + off);
+        fe_store(m + i, fe_add(m0, fe_mul(r, fe_sub(m1, m0))));
+        fe_store(d + i, fe_add(d0, fe_mul(r, fe_sub(d1, d0))));
+    }
+}
+
+static inline unsigned blocks_for(size_t n) {
+    size_t b = (n + SC_THREADS - 1) / SC_THREADS;
+    if (b > (size_t)SC_MAX_BLOCKS) b = SC_MAX_BLOCKS;
+    if (b == 0) b = 1;
+    return (unsigned)b;
+}
+static int fetch(const fe* dev, int count, hfe* out, cudaStream_t s) {
+    uint8_t tmp[16 * 4];
+    MLB_CUDA(cudaMemcpyAsync(tmp, dev, 16 * (size_t)count, cudaMemcpyDeviceToHost, s));
+    MLB_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < count; i++) out[i] = hfe_load(tmp + 16 * i);
+    return ML_OK;
+}
+
+int sumcheck_sums_launch(Ctx* ctx, const fe* m, const fe* d, size_t height, hfe* s1, hfe* s2, cudaStream_t s) {
+    (void)ctx;
+    const size_t off = height >> 1;
+    const unsigned nb = blocks_for(off);
+    fe* partials;
+    MLB_TRY(dev_alloc_async((void**)&partials, (size_t)(2 * nb + 2) * 16, s));
+    sumcheck_sums_kernel<<<nb, SC_THREADS, 0, s>>>(m, d, off, partials);
+    MLB_KERNEL_CHECK();
+    reduce_partials_kernel<<<1, 256, 0, s>>>(partials, (int)nb, 2, partials + 2 * nb);
+    MLB_KERNEL_CHECK();
+    hfe o[2];
+    MLB_TRY(fetch(partials + 2 * nb, 2, o, s));
+    MLB_TRY(dev_free_async(partials, s));
+    *s1 = o[0];
+    *s2 = o[1];
+    return ML_OK;
+}
+int sumcheck_partial_sum_launch(Ctx* ctx, const fe* m, const fe* d, size_t height, hfe r, hfe* out, cudaStream_t s) {
+    (void)ctx;
+    const size_t off = height >> 1;
+    const unsigned nb = blocks_for(off);
+    fe* partials;
+    MLB_TRY(dev_alloc_async((void**)&partials, (size_t)(nb + 1) * 16, s));
+    sumcheck_partial_kernel<<<nb, SC_THREADS, 0, s>>>(m, d, off, to_dev_fe_h(r), to_dev_fe_h(hfe_sub(1, r)), r == 1 ? 1 : 0, partials);
+    MLB_KERNEL_CHECK();
+    reduce_partials_kernel<<<1, 256, 0, s>>>(partials, (int)nb, 1, partials + nb);
+    MLB_KERNEL_CHECK();
+    MLB_TRY(fetch(partials + nb, 1, out, s));
+    MLB_TRY(dev_free_async(partials, s));
+    return ML_OK;
+}
+int sumcheck_fold_launch(fe* m, fe* d, size_t height, hfe r, cudaStream_t s) {
+    const size_t off = height >> 1;
+    if (off == 0) return ML_OK;
+    sumcheck_fold_kernel<<<blocks_for(off), 256, 0, s>>>(m, d, off, to_dev_fe_h(r));
+    MLB_KERNEL_CHECK();
+    return ML_OK;
+}
+
+}  // namespace mlb

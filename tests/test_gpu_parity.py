@@ -1,0 +1,364 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden vectors.  Bit-exact: every
+quantity on this path is integer / byte data."""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+from oracle import pyref as P
+from oracle.binding import fe_arr, fe_ints
+
+pytestmark = pytest.mark.gpu
+M = P.M
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+EDGE = [0, 1, 2, M - 1, M - 2, 2**64 - 1, 2**64, 2**64 + 1, 2**127, 2**96 - 1, 45 * 2**40 - 1, 45 * 2**40, 2**128 - 2**46 - 7, M - 2**40]
+
+
+# ------------------------------------------------------------------ field
+def test_field_ops_edge_and_random(ml, oracle):
+    rng = random.Random(21)
+    xs = [x for x in EDGE for _ in EDGE] + [rng.randrange(M) for _ in range(1 << 16)]
+    ys = [y for _ in EDGE for y in EDGE] + [rng.randrange(M) for _ in range(1 << 16)]
+    a, b = fe_arr(xs), fe_arr(ys)
+    for op, pyop in (("mul", lambda x, y: x * y % M), ("add", lambda x, y: (x + y) % M), ("sub", lambda x, y: (x - y) % M)):
+        got = getattr(ml, op)(a, b)
+        assert np.array_equal(got, oracle.vec(op, a, b)), op
+        assert fe_ints(got[:len(EDGE) ** 2]) == [pyop(x, y) for x, y in zip(xs[:len(EDGE) ** 2], ys[:len(EDGE) ** 2])]
+
+
+def test_field_mul_large_random(ml, oracle):
+    a, b = oracle.synthetic(1, 1 << 20), oracle.synthetic(2, 1 << 20)
+    assert np.array_equal(ml.mul(a, b), oracle.vec("mul", a, b))
+    # products whose high limbs are all-ones stress the carry chains
+    near = fe_arr([M - 1 - i for i in range(4096)])
+    assert np.array_equal(ml.mul(near, near[::-1].copy()), oracle.vec("mul", near, near[::-1].copy()))
+
+
+def test_field_inv_pow_from_i64(ml, oracle):
+    rng = random.Random(22)
+    xs = EDGE + [rng.randrange(M) for _ in range(500)]
+    assert ml.to_ints(ml.inv(xs)) == [P.inv(x) for x in xs]  # inv(0) = 0
+    e = rng.randrange(M)
+    assert ml.to_ints(ml.pow_(xs, e)) == [pow(x, e, M) for x in xs]
+    vals = [-1, -7, 0, 1, 2**40, -2**63, 2**63 - 1, -45 * 2**40]
+    assert ml.to_ints(ml.from_i64(vals)) == [P.from_i64(v) for v in vals]
+
+
+def test_synthetic_generator_matches_oracle(ml, oracle):
+    buf = ml.synthetic_elements_dev(0xB200, 5000)
+    ml.synchronize()
+    assert np.array_equal(buf.elems(), oracle.synthetic(0xB200, 5000))
+
+
+# ------------------------------------------------------------------ NTT
+def test_ntt_golden(ml, golden):
+    e = ml.ntt(list(range(8)), ml.pow_2_generator(3))
+    assert [str(x) for x in ml.to_ints(e)] == golden["ntt8"]
+    coeffs = ml.from_i64(range(1 << 10))
+    assert sha(ml.ntt(coeffs, ml.pow_2_generator(10)).tobytes()) == golden["ntt_1024_sha"]
+    assert sha(ml.reed_solomon(coeffs, ml.pow_2_generator(11)).tobytes()) == golden["rs_1024_sha"]
+
+
+@pytest.mark.parametrize("log_n", list(range(0, 16)) + [18, 19, 20])
+def test_ntt_intt_rs_all_sizes(ml, oracle, log_n):
+    n = 1 << log_n
+    x = oracle.synthetic(100 + log_n, n)
+    g = ml.pow_2_generator(log_n)
+    want = oracle.ntt(x, g) if n > 1 else x
+    got = ml.ntt(x, g)
+    assert np.array_equal(got, want)
+    assert np.array_equal(ml.intt(got, g), x)  # intt_test, src/ntt/mod.rs:192-201
+    if n > 1:
+        assert np.array_equal(ml.intt(got, g), oracle.intt(want, g))
+    g2 = ml.pow_2_generator(log_n + 1)
+    assert np.array_equal(ml.reed_solomon(x, g2), oracle.reed_solomon(x, g2))
+
+
+def test_ntt_inverse_generator_and_errors(ml, oracle):
+    x = oracle.synthetic(7, 1 << 13)
+    g = ml.pow_2_generator(13)
+    ginv = P.inv(g)
+    assert np.array_equal(ml.ntt(x, ginv), oracle.ntt(x, ginv))
+    assert np.array_equal(ml.intt(x, ginv), oracle.intt(x, ginv))
+    with pytest.raises(ml.NotPowerOfTwo):
+        ml.ntt(oracle.synthetic(1, 12), g)
+    with pytest.raises(ml.MlError):
+        ml.ntt(x, 12345)  # not a root of unity of that order
+
+
+def test_bit_reverse_and_powers(ml, oracle):
+    for n in (1, 2, 8, 1 << 12, 1 << 15):
+        x = oracle.synthetic(n, n)
+        assert np.array_equal(ml.bit_reverse_permutation(x), oracle.bit_reverse(x))
+    x = oracle.synthetic(3, 12)  # trailing_zeros(12) = 2: only the first 4 entries move
+    assert np.array_equal(ml.bit_reverse_permutation(x), oracle.bit_reverse(x))
+    for log in (0, 1, 5, 12, 13, 17):
+        assert np.array_equal(ml.pow_2_generator_powers(log), oracle.pow2_generator_powers(log))
+
+
+def test_polynomial_evaluate(ml, oracle):
+    rng = random.Random(5)
+    for n in (1, 5, 4096, 10000):
+        c = oracle.synthetic(n, n)
+        x = rng.randrange(M)
+        assert ml.polynomial_evaluate(c, x) == P.poly_eval(fe_ints(c), x)
+
+
+# ------------------------------------------------------------------ multilinear polynomials
+def test_mle_transforms(ml, oracle, golden):
+    e6 = ml.MultilinearPolynomialEvals([0, 1, 4, 8, 9, 3])
+    c6 = e6.to_coefficient()
+    assert [str(x) for x in ml.to_ints(c6.coeffs)] == golden["mle_conv6"]
+    assert np.array_equal(c6.to_evaluation().evals, e6.evals)  # multilinear_conversion_test
+    for log_n in (0, 1, 3, 11, 12, 13, 16, 20):
+        x = oracle.synthetic(40 + log_n, 1 << log_n)
+        c = ml.MultilinearPolynomialEvals(x).to_coefficient()
+        assert np.array_equal(c.coeffs, oracle.to_coefficient(x)), log_n
+        assert np.array_equal(c.to_evaluation().evals, x)
+
+
+def test_mle_evaluate(ml, oracle):
+    rng = random.Random(9)
+    for nv in (0, 1, 4, 12, 13, 15):
+        ev = oracle.synthetic(60 + nv, 1 << nv)
+        args = fe_arr([rng.randrange(M) for _ in range(nv)]) if nv else np.zeros((0, 16), dtype=np.uint8)
+        want = oracle.mle_evals_evaluate(ev, args) if nv else fe_ints(ev)[0]
+        assert ml.MultilinearPolynomialEvals(ev).evaluate(ml.to_ints(args)) == want
+        co = oracle.to_coefficient(ev)
+        assert ml.MultilinearPolynomial(co).evaluate(ml.to_ints(args)) == want
+    e6 = ml.MultilinearPolynomialEvals([0, 1, 4, 8, 9, 3])  # len 6 -> next_power_of_two = 8 = 2^3
+    args = [rng.randrange(M) for _ in range(3)]
+    assert e6.evaluate(args) == P.mle_evals_evaluate([0, 1, 4, 8, 9, 3], args)
+    with pytest.raises(ml.SizeMismatch):
+        e6.evaluate(args[:2])
+
+
+# ------------------------------------------------------------------ Merkle
+def test_merkle_reference_tests(ml, golden):
+    d0 = np.array([[0], [8], [4], [1], [5], [7], [6], [1]], dtype=np.uint8)
+    d1 = np.array([[1], [3], [2], [3], [2], [1], [2], [3]], dtype=np.uint8)
+    m = ml.Merkle.commit(d0)
+    assert m.root().hex() == golden["merkle_test_root"]
+    value, path = m.open(5)
+    assert value == bytes([7]) and ml.path_verify(value, path, m.root(), 5) == 0  # merkle_test
+    assert m.open(8) is None
+    mb = ml.Merkle.batch_commit([d0, d1])
+    assert mb.root().hex() == golden["batched_merkle_test_root"]
+    v5, p5 = mb.batch_open(5)
+    assert v5 == bytes([7, 1]) and ml.path_verify(v5, p5, mb.root(), 5) == 0
+    v2, p2 = mb.batch_open(2)
+    assert v2 == bytes([4, 2]) and ml.path_verify(v2, p2, mb.root(), 2) == 0 and ml.path_verify(v2, p2, mb.root(), 1) != 0
+    vec = [[[0, 4], [8, 2], [4, 9], [1, 3], [5, 7], [7, 2], [6, 8], [1, 5]], [[9, 3], [2, 7], [6, 1], [3, 8], [4, 2], [8, 5], [1, 9], [7, 4]],
+           [[3, 6], [5, 1], [8, 3], [2, 9], [7, 5], [1, 8], [4, 3], [6, 2]], [[7, 1], [3, 9], [5, 2], [8, 6], [1, 4], [9, 7], [2, 5], [4, 8]]]
+    mv = ml.Merkle.batch_commit([np.array(b, dtype=np.uint8) for b in vec])
+    assert mv.root().hex() == golden["batched_merkle_with_vectors_test_root"]
+    with pytest.raises(ml.NotPowerOfTwo):
+        ml.Merkle.commit(d0[:6])
+    with pytest.raises(ml.SizeMismatch):
+        ml.Merkle.batch_commit([])
+
+
+@pytest.mark.parametrize("n_items,item_bytes", [(1, 32), (2, 32), (8, 7), (64, 55), (64, 56), (1024, 64), (4096, 100), (16384, 32)])
+def test_merkle_generic_items(ml, oracle, n_items, item_bytes):
+    rng = np.random.default_rng(n_items + item_bytes)
+    data = rng.integers(0, 256, size=(n_items, item_bytes), dtype=np.uint8)
+    m, om = ml.Merkle.commit(data), oracle.merkle_commit(data)
+    assert m.root() == om.root()
+    for a, b in zip(m.layers, om.layers()):
+        assert np.array_equal(a, b)
+    for idx in {0, n_items - 1, n_items // 3}:
+        assert m.open(idx) == om.open(idx)
+
+
+# ------------------------------------------------------------------ FRI
+def test_fri_golden(ml, golden):
+    g = golden["fri_log10"]
+    vals = ml.from_i64([7 * i + 3 for i in range(1 << 10)])
+    gp = ml.pow_2_generator_powers(11)
+    code = ml.reed_solomon(vals, ml.to_ints(gp[1:2])[0])
+    t = ml.Transcript()
+    proof = ml.FriProof.prove(code, gp, t)
+    assert [c.hex() for c in proof.commitments] == g["commitments"]
+    assert str(proof.last_elem) == g["last_elem"] and proof.last_random.hex() == g["last_random"]
+    blob = proof.serialize()
+    assert len(blob) == g["blob_len"] and sha(blob) == g["blob_sha"]
+    assert proof.verify() == 0  # prove_and_verify_test
+    t2 = ml.Transcript()
+    p2 = ml.FriProof.prove_from_coeffs(vals, t2)  # fused reed_solomon + prove
+    assert p2.serialize() == blob and t2.random() == t.random()
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 7, 12, 13, 16])
+def test_fri_stepwise_vs_oracle(ml, oracle, log_n):
+    n = 1 << log_n  # message length; code has 2n elements
+    coeffs = oracle.synthetic(70 + log_n, n)
+    gp = oracle.pow2_generator_powers(log_n + 1)
+    code = oracle.reed_solomon(coeffs, fe_ints(gp[1:2])[0])
+    t, ot = ml.Transcript(), oracle.transcript()
+    f, of = ml.FriProverData.init(code, t), oracle.fri_init(code, ot)
+    for k in range(log_n):
+        r = t.next_challenge()
+        assert r == ot.next_challenge()
+        f.fold_step(gp, k, r, t)
+        assert of.fold_step(gp, k, r, ot) == 0
+    assert f.num_trees() == of.num_trees() == log_n
+    assert f.fold_roots() == of.roots() and f.last_element == of.last_element() and f.last_element is not None
+    for j in range(f.num_trees()):
+        assert np.array_equal(f.tree_data(j), of.tree_data(j)), j
+        for a, b in zip(f.tree(j).layers, of.tree(j).layers()):
+            assert np.array_equal(a, b)
+    assert t.random() == ot.random()
+    idx = (12345 * log_n) % n
+    q = f.open_query_at(idx)
+    cur, cur_n = idx, n
+    for j, (value, path) in enumerate(q):
+        assert (value, path) == of.tree(j).open(cur)
+        cur_n //= 2
+        cur = cur % cur_n if cur_n else 0
+
+
+def test_fri_prove_vs_oracle_and_errors(ml, oracle):
+    log_n = 14
+    coeffs = oracle.synthetic(5, 1 << log_n)
+    gp = oracle.pow2_generator_powers(log_n + 1)
+    code = oracle.reed_solomon(coeffs, fe_ints(gp[1:2])[0])
+    t, ot = ml.Transcript(), oracle.transcript()
+    proof = ml.FriProof.prove(code, gp, t)
+    oproof, st = oracle.fri_prove(code, gp, ot)
+    assert st == 0 and proof.serialize() == oproof.blob and proof.verify() == 0 and t.random() == ot.random()
+    bad = oracle.synthetic(6, 1 << 8)  # random data is not a codeword: assert "not an RS code"
+    with pytest.raises(ml.NotRsCode):
+        ml.FriProof.prove(bad, None, ml.Transcript())
+    with pytest.raises(ml.NotPowerOfTwo):
+        ml.FriProverData.init(oracle.synthetic(1, 24), ml.Transcript())
+    with pytest.raises(ml.SizeMismatch):
+        ml.FriProof.prove(code, gp[:100], ml.Transcript())
+
+
+# ------------------------------------------------------------------ sumcheck
+@pytest.mark.parametrize("nv", [1, 2, 5, 12, 13, 16])
+def test_sumcheck_tables_and_rounds(ml, oracle, nv):
+    rng = random.Random(nv)
+    ev = oracle.synthetic(80 + nv, 1 << nv)
+    inp = fe_arr([rng.randrange(M) for _ in range(nv)])
+    s, os_ = ml.SumcheckTables.build_tables_for_pcs(inp, ev), oracle.sumcheck_build(inp, ev)
+    for a, b in zip(s.tables(), os_.tables()):
+        assert np.array_equal(a, b)
+    for r in (1, 2, 3, rng.randrange(M)):
+        assert s.partial_sum(r) == os_.partial_sum(r)
+    claim = oracle.mle_evals_evaluate(ev, inp)
+    t, ot = ml.Transcript(), oracle.transcript()
+    nz, r, prev = s.compute_sumcheck_polynomial(2, claim, t)
+    onz, orr, oprev = os_.compute_sumcheck_polynomial(2, claim, ot)
+    assert (nz, r, prev) == (onz, orr, oprev) and s.height == os_.height()
+    for a, b in zip(s.tables(), os_.tables()):
+        assert np.array_equal(a, b)
+    rr = rng.randrange(M)
+    if s.height > 1:
+        s.fold(rr), os_.fold(rr)
+        for a, b in zip(s.tables(), os_.tables()):
+            assert np.array_equal(a, b)
+    s2, os2 = ml.SumcheckTables.build_tables_for_pcs(inp, ev), oracle.sumcheck_build(inp, ev)
+    t, ot = ml.Transcript(), oracle.transcript()
+    assert s2.compute_sumcheck_polynomials(1, t, claim) == os2.compute_sumcheck_polynomials(1, ot, claim)
+    assert t.random() == ot.random()
+
+
+def test_sumcheck_general_degree_and_errors(ml, oracle):
+    ev = oracle.synthetic(3, 1 << 6)
+    inp = fe_arr(list(range(3, 9)))
+    s, os_ = ml.SumcheckTables.build_tables_for_pcs(inp, ev), oracle.sumcheck_build(inp, ev)
+    t, ot = ml.Transcript(), oracle.transcript()
+    assert s.compute_sumcheck_polynomial(3, 12345, t) == os_.compute_sumcheck_polynomial(3, 12345, ot)
+    with pytest.raises(ml.SizeMismatch):
+        ml.SumcheckTables.build_tables_for_pcs(inp[:5], ev)
+
+
+# ------------------------------------------------------------------ PCS
+def test_pcs_golden(ml, golden):
+    g = golden["pcs_nv8"]
+    nv = 8
+    evals = ml.MultilinearPolynomialEvals(ml.from_i64([7 * i + 3 for i in range(1 << nv)]))
+    inputs = ml.from_i64(range(nv))
+    out = evals.evaluate(ml.to_ints(inputs))
+    assert str(out) == g["output"]
+    t = ml.Transcript()
+    proof = ml.PCSProof.prove(inputs, out, evals, t)
+    assert proof.fri_proof.commitments[0].hex() == g["root0"] and str(proof.fri_proof.last_elem) == g["last_elem"]
+    assert [[str(c) for c in nz] for nz in proof.sumcheck_polynomials] == g["sumcheck"]
+    assert sha(proof.fri_proof.serialize()) == g["blob_sha"] and t.random().hex() == g["final_random"]
+    assert proof.verify(ml.Transcript()) == 0
+
+
+@pytest.mark.parametrize("nv", [1, 2, 3, 9, 13, 16])
+def test_pcs_prove_vs_oracle(ml, oracle, nv):
+    rng = random.Random(nv)
+    ev = oracle.synthetic(90 + nv, 1 << nv)
+    inp = fe_arr([rng.randrange(M) for _ in range(nv)])
+    out = oracle.mle_evals_evaluate(ev, inp)
+    t, ot = ml.Transcript(), oracle.transcript()
+    proof = ml.PCSProof.prove(inp, out, ev, t)
+    oproof, st = oracle.pcs_prove(inp, out, ev, ot)
+    assert st == 0
+    assert proof.fri_proof.serialize() == oproof.fri.blob
+    assert [c for nz in proof.sumcheck_polynomials for c in nz] == oproof.sumcheck
+    assert t.random() == ot.random()
+    assert proof.verify(ml.Transcript()) == 0 and oproof.verify(oracle.transcript()) == 0
+    wrong = ml.PCSProof.prove(inp, (out + 1) % M, ev, ml.Transcript())  # a false claim must not verify
+    assert wrong.verify(ml.Transcript()) == 107
+
+
+def test_pcs_reference_test_inputs_n20(ml, oracle):
+    """multilinear_pcs_bench_test (multilinear_pcs.rs:211-228): n_vars = 20, evals 7i+3, inputs i — BASELINE config 1"""
+    nv = 20
+    ev = ml.from_i64([7 * i + 3 for i in range(1 << nv)])
+    inp = ml.from_i64(range(nv))
+    out = ml.MultilinearPolynomialEvals(ev).evaluate(ml.to_ints(inp))
+    t, ot = ml.Transcript(), oracle.transcript()
+    proof = ml.PCSProof.prove(inp, out, ev, t)
+    assert proof.verify(ml.Transcript()) == 0
+    oproof, st = oracle.pcs_prove(inp, out, ev, ot)
+    assert st == 0 and hashlib.sha256(proof.fri_proof.serialize()).digest() == hashlib.sha256(oproof.fri.blob).digest()
+    assert [c for nz in proof.sumcheck_polynomials for c in nz] == oproof.sumcheck and t.random() == ot.random()
+
+
+# ------------------------------------------------------------------ batched
+def test_batched_golden(ml, golden):
+    g = golden["bfri_log6_b4"]
+    gp = ml.pow_2_generator_powers(7)
+    gen = ml.to_ints(gp[1:2])[0]
+    codes = [ml.reed_solomon(ml.from_i64([7 * i + 3 + 100 * j for i in range(64)]), gen) for j in range(4)]
+    proof = ml.BatchedFriProof.prove(codes, gp, ml.Transcript())
+    assert proof.batch_commitment.hex() == g["batch_commitment"] and [c.hex() for c in proof.commitments] == g["commitments"]
+    assert str(proof.last_elem) == g["last_elem"] and sha(proof.serialize()) == g["blob_sha"] and proof.verify() == 0
+
+    g = golden["bpcs_nv6_b10"]
+    nv, B = 6, 10
+    polys = [fe_arr([(j * 3 + i * 5) % 100 for j in range(1 << nv)]) for i in range(B)]
+    inputs = ml.from_i64(range(nv))
+    outputs = [ml.MultilinearPolynomialEvals(p).evaluate(ml.to_ints(inputs)) for p in polys]
+    assert [str(o) for o in outputs] == g["outputs"]
+    proof = ml.BatchedPCSProof.prove(inputs, outputs, polys, ml.Transcript())
+    assert proof.fri_proof.batch_commitment.hex() == g["batch_commitment"]
+    assert [[str(c) for c in nz] for nz in proof.sumcheck_polynomials] == g["sumcheck"]
+    assert sha(proof.fri_proof.serialize()) == g["blob_sha"] and proof.verify(ml.Transcript()) == 0
+
+
+@pytest.mark.parametrize("nv,B", [(2, 1), (3, 2), (5, 3), (10, 7), (12, 64), (14, 5)])
+def test_batched_pcs_vs_oracle(ml, oracle, nv, B):
+    rng = random.Random(nv * 100 + B)
+    polys = [oracle.synthetic(1000 * B + j, 1 << nv) for j in range(B)]
+    inp = fe_arr([rng.randrange(M) for _ in range(nv)])
+    outs = fe_arr([oracle.mle_evals_evaluate(p, inp) for p in polys])
+    t, ot = ml.Transcript(), oracle.transcript()
+    proof = ml.BatchedPCSProof.prove(inp, outs, polys, t)
+    oproof, st = oracle.batched_pcs_prove(inp, outs, polys, ot)
+    assert st == 0 and proof.fri_proof.serialize() == oproof.fri.blob
+    assert [c for nz in proof.sumcheck_polynomials for c in nz] == oproof.sumcheck
+    assert t.random() == ot.random() and proof.verify(ml.Transcript()) == 0
