@@ -228,7 +228,15 @@ int ml_bpcs_proof_sumcheck_coeffs(const ml_bpcs_proof *p, uint8_t *out);
 int ml_batched_leaf_subtree_dev(const void *const *pairs_dev, size_t n_codes, size_t leaf_count, void *stream, uint8_t root_out[32]);
 int ml_merkle_top_from_roots(const uint8_t *roots, size_t n_roots, uint8_t root_out[32]);
 
-/* ---- instrumentation for bench.py: time of the last phases in ms (CUDA events on the library stream) ---- */
+/* ---- instrumentation for bench.py ----
+ * ml_profile_*: when enabled, every kernel group is bracketed by CUDA events on its launch stream;
+ * ml_profile_get sums device time, launches and algorithmic HBM bytes (input read once + output written once)
+ * per group id: 0 ntt_pass, 1 merkle_leaf_subtree, 2 merkle_nodes, 3 merkle_top, 4 fri_fold, 5 sumcheck_sums,
+ * 6 sumcheck_fold, 7 mobius, 8 eq_table, 9 bit_reverse, 10 query_gather.
+ * ml_microbench: integer-pipe speed-of-light loops ("modmul", "butterfly", "sha_leaf", "sha_node", "copy"). */
+int ml_profile_enable(int on);
+int ml_profile_reset(void);
+int ml_profile_get(int id, double *total_ms, uint64_t *launches, double *alg_bytes);
 int ml_microbench(const char *what, size_t n, int iters, double *ms_out, double *work_out);
 
 #ifdef __cplusplus

@@ -15,6 +15,28 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// ---- per-kernel timing registry
+bool g_prof_on = false;
+struct ProfRec { int id; double bytes; cudaEvent_t e0, e1; bool closed; };
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t prof_event() {
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_record(int id, double alg_bytes, cudaStream_t s, bool end) {
+    if (!end) {
+        ProfRec r{id, alg_bytes, prof_event(), prof_event(), false};
+        cudaEventRecord(r.e0, s);
+        g_prof.push_back(r);
+    } else {
+        for (size_t i = g_prof.size(); i-- > 0;)
+            if (g_prof[i].id == id && !g_prof[i].closed) { cudaEventRecord(g_prof[i].e1, s); g_prof[i].closed = true; break; }
+    }
+}
+
 static std::mutex g_ctx_mu;
 static std::map<int, Ctx*> g_ctx;
 
@@ -89,6 +111,25 @@ int ml_device_name(char* out, size_t cap) {
 }
 int ml_synchronize(void) { MLB_CUDA(cudaDeviceSynchronize()); return ML_OK; }
 uint64_t ml_kernel_launches(void) { return g_kernel_launches; }
+
+int ml_profile_enable(int on) { g_prof_on = on != 0; return ML_OK; }
+int ml_profile_reset(void) {
+    for (auto& r : g_prof) { g_event_pool.push_back(r.e0); g_event_pool.push_back(r.e1); }
+    g_prof.clear();
+    return ML_OK;
+}
+int ml_profile_get(int id, double* total_ms, uint64_t* launches, double* alg_bytes) {
+    MLB_CUDA(cudaDeviceSynchronize());
+    double ms = 0, bytes = 0;
+    uint64_t n = 0;
+    for (auto& r : g_prof) {
+        if (r.id != id || !r.closed) continue;
+        float t = 0;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { ms += t; bytes += r.bytes; n++; }
+    }
+    *total_ms = ms; *launches = n; *alg_bytes = bytes;
+    return ML_OK;
+}
 
 int ml_dev_alloc(size_t bytes, void** out) { MLB_CUDA(cudaMalloc(out, bytes ? bytes : 16)); return ML_OK; }
 int ml_dev_free(void* p) { MLB_CUDA(cudaFree(p)); return ML_OK; }

@@ -48,6 +48,7 @@ int fri_fold_launch(Ctx* ctx, const fe* cur, size_t n_cur, fe* next, hfe r, size
     const RootTables* rt;
     MLB_TRY(get_root_tables(ctx, log_n0, s, &rt));
     const size_t half_n = n_cur / 2;
+    ProfScope prof(PROF_FRI_FOLD, 24.0 * (double)n_cur, s);  // read n elements, write n/2
     fri_fold_kernel<<<grid_for(half_n), 256, 0, s>>>(cur, half_n, next, to_dev_fe(hfe_half(r)), (int)k, log_n0, rt->lo, rt->hi);
     MLB_KERNEL_CHECK();
     return ML_OK;
@@ -78,6 +79,7 @@ int fri_batched_fold_launch(Ctx* ctx, const fe* const* codes, size_t n_codes, si
     const RootTables* rt;
     MLB_TRY(get_root_tables(ctx, log_n0, s, &rt));
     const size_t half_n = n / 2;
+    ProfScope prof(PROF_FRI_FOLD, 16.0 * (double)n * (double)n_codes + 8.0 * (double)n, s);
     fri_batched_fold_kernel<<<grid_for(half_n), 256, 0, s>>>(codes, (int)n_codes, half_n, next, to_dev_fe(fingerprint_r),
                                                               to_dev_fe(hfe_half(r)), log_n0, rt->lo, rt->hi);
     MLB_KERNEL_CHECK();

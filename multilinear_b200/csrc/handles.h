@@ -23,6 +23,7 @@ struct ml_merkle {
     bool owns_digests = true;
     uint8_t root[32];
     int device = 0;
+    cudaStream_t stream = nullptr;  // stream-ordered allocations are returned to the pool on this stream
 };
 
 struct ml_fri {
@@ -36,6 +37,7 @@ struct ml_fri {
     bool has_last = false;
     mlb::hfe last = 0;
     int log_n0 = 0;  // log2 of the original domain (gen_pows.len())
+    cudaStream_t stream = nullptr;
 };
 
 struct PathH {
@@ -56,6 +58,7 @@ struct ml_sumcheck {
     mlb::fe* matrix = nullptr;
     mlb::fe* delta = nullptr;
     size_t height = 0;
+    cudaStream_t stream = nullptr;
 };
 struct ml_pcs_proof {
     ml_fri_proof fri;

@@ -42,6 +42,17 @@ extern unsigned long long g_kernel_launches;
         }                                                                                       \
     } while (0)
 
+// ------------------------------------------------------------------ optional per-kernel timing (CUDA events on the launch stream)
+enum ProfId { PROF_NTT_PASS = 0, PROF_MERKLE_LEAF, PROF_MERKLE_NODES, PROF_MERKLE_TOP, PROF_FRI_FOLD, PROF_SUMCHECK_SUMS,
+              PROF_SUMCHECK_FOLD, PROF_MOBIUS, PROF_EQ_TABLE, PROF_BITREV, PROF_GATHER, PROF_COUNT };
+extern bool g_prof_on;
+void prof_record(int id, double alg_bytes, cudaStream_t s, bool end);
+struct ProfScope {  // brackets the kernel launches issued inside its lifetime
+    int id; cudaStream_t s; bool on;
+    ProfScope(int id_, double alg_bytes, cudaStream_t s_) : id(id_), s(s_), on(g_prof_on) { if (on) prof_record(id, alg_bytes, s, false); }
+    ~ProfScope() { if (on) prof_record(id, 0, s, true); }
+};
+
 // ------------------------------------------------------------------ host scalar field (transcript challenges,
 // round polynomials, root-of-unity parameters).  Scalars only: all array work is on the GPU.
 typedef unsigned __int128 hfe;

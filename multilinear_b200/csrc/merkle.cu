@@ -155,11 +155,13 @@ static int upper_from(uint8_t* digests, size_t n_leaves, int from_layer, cudaStr
     while (layer < total) {
         size_t count = n_leaves >> layer;
         if (count <= 4096) {
+            ProfScope prof(PROF_MERKLE_TOP, 64.0 * (double)count, s);
             merkle_top_kernel<<<1, 256, 0, s>>>(digests, n_leaves, layer);
             MLB_KERNEL_CHECK();
             return ML_OK;
         }
         size_t threads = count >> 3;
+        ProfScope prof(PROF_MERKLE_NODES, 60.0 * (double)count, s);  // read 32 B/digest, write 3 layers (28 B/digest)
         merkle_nodes_kernel<3><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(digests, n_leaves, layer);
         MLB_KERNEL_CHECK();
         layer += 3;
@@ -173,8 +175,11 @@ int merkle_rs_launch(const fe* code, size_t n_code, uint8_t* digests, cudaStream
     if (L == 0) return ML_ERR_NOT_POW2;
     if (L >= 8) {
         size_t threads = L >> 3;
-        merkle_rs_kernel<3><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(code, L, digests);
-        MLB_KERNEL_CHECK();
+        {   // read one 32-byte pair per leaf, write layers 0..3 (32 * (1 + 1/2 + 1/4 + 1/8) bytes per leaf)
+            ProfScope prof(PROF_MERKLE_LEAF, 92.0 * (double)L, s);
+            merkle_rs_kernel<3><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(code, L, digests);
+            MLB_KERNEL_CHECK();
+        }
         return upper_from(digests, L, 3, s);
     }
     merkle_rs_kernel<0><<<1, 128, 0, s>>>(code, L, digests);
@@ -185,14 +190,20 @@ int merkle_rs_launch(const fe* code, size_t n_code, uint8_t* digests, cudaStream
 int merkle_batched_rs_launch(const fe* const* codes, size_t n_codes, size_t n_code, uint8_t* digests, cudaStream_t s) {
     const size_t L = n_code / 2;
     if (L == 0 || n_codes == 0) return ML_ERR_NOT_POW2;
-    merkle_batched_kernel<false><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(codes, (int)n_codes, L, digests);
-    MLB_KERNEL_CHECK();
+    {
+        ProfScope prof(PROF_MERKLE_LEAF, (32.0 * (double)n_codes + 32.0) * (double)L, s);
+        merkle_batched_kernel<false><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(codes, (int)n_codes, L, digests);
+        MLB_KERNEL_CHECK();
+    }
     return upper_from(digests, L, 0, s);
 }
 int merkle_batched_pairs_launch(const uint8_t* const* pairs, size_t n_codes, size_t n_leaves, uint8_t* digests, cudaStream_t s) {
     if (n_leaves == 0 || n_codes == 0) return ML_ERR_NOT_POW2;
-    merkle_batched_kernel<true><<<(unsigned)((n_leaves + 127) / 128), 128, 0, s>>>((const fe* const*)pairs, (int)n_codes, n_leaves, digests);
-    MLB_KERNEL_CHECK();
+    {
+        ProfScope prof(PROF_MERKLE_LEAF, (32.0 * (double)n_codes + 32.0) * (double)n_leaves, s);
+        merkle_batched_kernel<true><<<(unsigned)((n_leaves + 127) / 128), 128, 0, s>>>((const fe* const*)pairs, (int)n_codes, n_leaves, digests);
+        MLB_KERNEL_CHECK();
+    }
     return upper_from(digests, n_leaves, 0, s);
 }
 int merkle_bytes_launch(const uint8_t* const* data, size_t n_batches, size_t item_bytes, size_t n_items, uint8_t* digests, cudaStream_t s) {

@@ -92,6 +92,7 @@ int mobius_launch(const fe* in, fe* out, size_t len, bool subtract, cudaStream_t
     }
     MLB_CUDA(cudaFuncSetAttribute(mobius_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     MLB_CUDA(cudaFuncSetAttribute(mobius_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    ProfScope prof(PROF_MOBIUS, 32.0 * (double)span, s);
     int bit_lo = 0;
     const fe* src = in;
     // first pass: low min(n,12) bits, contiguous tiles; then groups of <= 8 bits with T = 4096 >> bits columns
@@ -236,6 +237,7 @@ int eq_table_launch(Ctx* ctx, const hfe* inputs, size_t n_vars, fe* delta, cudaS
     const size_t n = (size_t)1 << n_vars;
     size_t blocks = (n + 255) / 256;
     if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
+    ProfScope prof(PROF_EQ_TABLE, 16.0 * (double)n, s);
     outer_product_kernel<<<(unsigned)blocks, 256, 0, s>>>(wh, wl, lb, n, delta);
     MLB_KERNEL_CHECK();
     return dev_free_async(scratch, s);

@@ -265,6 +265,8 @@ int ntt_launch(Ctx* ctx, const fe* in, fe* out, int log_n, bool inverse, bool rs
     fe* tmp = nullptr;
     if (n_passes > 1) MLB_TRY(dev_alloc_async((void**)&tmp, ((size_t)16) << log_n, s));
 
+    const double nbytes = 16.0 * (double)((size_t)1 << log_n);
+    ProfScope prof(PROF_NTT_PASS, rs_zero_padded ? 1.5 * nbytes : 2.0 * nbytes, s);  // read input once + write output once
     PassArgs a;
     memset(&a, 0, sizeof a);
     a.small = inverse ? ctx->small_inv : ctx->small_fwd;
@@ -315,6 +317,7 @@ int bit_reverse_launch(const void* in, void* out, size_t n, size_t elem_bytes, c
     int bits = __builtin_ctzll((unsigned long long)n);
     size_t blocks = (n + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
+    ProfScope prof(PROF_BITREV, 32.0 * (double)n, s);
     bit_reverse_kernel<<<(unsigned)blocks, 256, 0, s>>>((const uint4*)in, (uint4*)out, n, bits);
     MLB_KERNEL_CHECK();
     return ML_OK;

@@ -24,6 +24,10 @@ struct Scratch {
     template <class T> T* as() { return (T*)p; }
 };
 
+// handle-owned buffers come from the stream-ordered pool (cudaMalloc/cudaFree would serialise the device per layer)
+int pmalloc(void** p, size_t bytes, cudaStream_t s) { return dev_alloc_async(p, bytes, s); }
+void pfree(void* p, cudaStream_t s) { if (p) cudaFreeAsync(p, s); }
+
 int h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
     if (bytes) MLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
     return ML_OK;
@@ -90,17 +94,17 @@ __global__ void gather_batch_values_kernel(const fe* const* __restrict__ codes, 
 
 void free_merkle(ml_merkle* m) {
     if (!m) return;
-    if (m->owns_digests && m->digests) cudaFree(m->digests);
+    if (m->owns_digests) pfree(m->digests, m->stream);
     if (m->owns_data)
-        for (void* p : m->data) cudaFree(p);
-    if (m->data_ptrs_dev) cudaFree(m->data_ptrs_dev);
+        for (void* p : m->data) pfree(p, m->stream);
+    pfree(m->data_ptrs_dev, m->stream);
     delete m;
 }
-int new_merkle(size_t n_leaves, ml_merkle** out) {
+int new_merkle(size_t n_leaves, cudaStream_t s, ml_merkle** out) {
     ml_merkle* m = new ml_merkle();
     m->n_leaves = n_leaves;
-    cudaError_t e = cudaMalloc((void**)&m->digests, (2 * n_leaves) * 32);
-    if (e != cudaSuccess) { delete m; set_error("digest allocation failed: %s", cudaGetErrorString(e)); return ML_ERR_ALLOC; }
+    m->stream = s;
+    if (pmalloc((void**)&m->digests, (2 * n_leaves) * 32, s) != ML_OK) { delete m; return ML_ERR_ALLOC; }
     cudaGetDevice(&m->device);
     *out = m;
     return ML_OK;
@@ -110,14 +114,14 @@ int merkle_fetch_root(ml_merkle* m, cudaStream_t s) {
     return d2h_sync(m->root, m->digests + 32 * merkle_layer_offset(m->n_leaves, top), 32, s);
 }
 int merkle_set_ptrs(ml_merkle* m, cudaStream_t s) {
-    MLB_CUDA(cudaMalloc((void**)&m->data_ptrs_dev, m->data.size() * sizeof(void*)));
+    MLB_TRY(pmalloc((void**)&m->data_ptrs_dev, m->data.size() * sizeof(void*), s));
     return h2d(m->data_ptrs_dev, m->data.data(), m->data.size() * sizeof(void*), s);
 }
 
 // FRI layer commit: commit_rs_code (src/fri/mod.rs:45-55) + absorb root (:71, :133)
 int fri_commit_layer(ml_fri* f, fe* code, size_t n, bool owns_code, ml_transcript* t, cudaStream_t s) {
     ml_merkle* m;
-    MLB_TRY(new_merkle(n / 2, &m));
+    MLB_TRY(new_merkle(n / 2, s, &m));
     m->kind = ml_merkle::RS_CODE;
     m->item_bytes = 32;
     m->data.push_back(code);
@@ -134,7 +138,7 @@ int fri_commit_layer(ml_fri* f, fe* code, size_t n, bool owns_code, ml_transcrip
 void free_fri(ml_fri* f) {
     if (!f) return;
     for (auto& L : f->layers) {
-        if (L.owns_code && L.code) cudaFree(L.code);
+        if (L.owns_code) pfree(L.code, f->stream);
         free_merkle(L.tree);
     }
     delete f;
@@ -144,7 +148,7 @@ int fold_finish(ml_fri* f, fe* next, size_t half_n, ml_transcript* t, cudaStream
     if (half_n == ((size_t)1 << ML_LOG_BLOWUP)) {
         uint8_t b[32];
         int st = d2h_sync(b, next, 32, s);
-        cudaFree(next);
+        pfree(next, s);
         MLB_TRY(st);
         if (memcmp(b, b + 16, 16) != 0) { set_error("not an RS code"); return ML_ERR_NOT_RS_CODE; }
         f->last = hfe_load(b);
@@ -153,7 +157,7 @@ int fold_finish(ml_fri* f, fe* next, size_t half_n, ml_transcript* t, cudaStream
         return ML_OK;
     }
     int st = fri_commit_layer(f, next, half_n, true, t, s);
-    if (st != ML_OK) cudaFree(next);
+    if (st != ML_OK) pfree(next, s);
     return st;
 }
 int fri_fold_step_impl(Ctx* ctx, ml_fri* f, size_t k, hfe r, ml_transcript* t, cudaStream_t s) {
@@ -164,16 +168,17 @@ int fri_fold_step_impl(Ctx* ctx, ml_fri* f, size_t k, hfe r, ml_transcript* t, c
     const size_t half_n = n >> 1;
     if ((half_n << k) > ((size_t)1 << f->log_n0)) { set_error("fold_step: k = %zu out of range for this domain", k); return ML_ERR_ARG; }
     fe* next;
-    MLB_CUDA(cudaMalloc((void**)&next, half_n * 16));
+    MLB_TRY(pmalloc((void**)&next, half_n * 16, s));
     int st = fri_fold_launch(ctx, last.code, n, next, r, k, f->log_n0, s);
-    if (st != ML_OK) { cudaFree(next); return st; }
+    if (st != ML_OK) { pfree(next, s); return st; }
     return fold_finish(f, next, half_n, t, s);
 }
 int fri_init_owned(ml_fri** out, fe* code, size_t n, bool owns, ml_transcript* t, cudaStream_t s) {
     ml_fri* f = new ml_fri();
     f->log_n0 = (int)ilog2(n);
+    f->stream = s;
     int st = fri_commit_layer(f, code, n, owns, t, s);
-    if (st != ML_OK) { if (owns) cudaFree(code); free_fri(f); return st; }
+    if (st != ML_OK) { if (owns) pfree(code, s); free_fri(f); return st; }
     *out = f;
     return ML_OK;
 }
@@ -234,6 +239,7 @@ int fri_open_queries(const ml_fri* f, const std::vector<size_t>& indices, std::v
     MLB_TRY(djobs.alloc(jobs.size() * sizeof(PathJob)));
     MLB_TRY(dout.alloc(off));
     MLB_TRY(h2d(djobs.p, jobs.data(), jobs.size() * sizeof(PathJob), s));
+    ProfScope prof(PROF_GATHER, 2.0 * (double)off, s);
     gather_paths_kernel<<<(unsigned)jobs.size(), 64, 0, s>>>(djobs.as<PathJob>(), dout.as<uint8_t>());
     MLB_KERNEL_CHECK();
     std::vector<uint8_t> host(off);
@@ -318,8 +324,8 @@ int sumcheck_round(Ctx* ctx, ml_sumcheck* sc, size_t total_degree, hfe* previous
 }
 void free_sumcheck(ml_sumcheck* s) {
     if (!s) return;
-    if (s->matrix) cudaFree(s->matrix);
-    if (s->delta) cudaFree(s->delta);
+    pfree(s->matrix, s->stream);
+    pfree(s->delta, s->stream);
     delete s;
 }
 int sumcheck_build(Ctx* ctx, const uint8_t* inputs, size_t n_vars, const void* evals, bool evals_on_device, size_t height, cudaStream_t s,
@@ -327,9 +333,9 @@ int sumcheck_build(Ctx* ctx, const uint8_t* inputs, size_t n_vars, const void* e
     if (n_vars >= 40 || ((size_t)1 << n_vars) != height) { set_error("assert_eq!(1 << n_vars, height) failed"); return ML_ERR_SIZE; }
     ml_sumcheck* sc = new ml_sumcheck();
     sc->height = height;
-    if (cudaMalloc((void**)&sc->matrix, height * 16) != cudaSuccess || cudaMalloc((void**)&sc->delta, height * 16) != cudaSuccess) {
+    sc->stream = s;
+    if (pmalloc((void**)&sc->matrix, height * 16, s) != ML_OK || pmalloc((void**)&sc->delta, height * 16, s) != ML_OK) {
         free_sumcheck(sc);
-        set_error("sumcheck table allocation failed");
         return ML_ERR_ALLOC;
     }
     cudaError_t e = cudaMemcpyAsync(sc->matrix, evals, height * 16, evals_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s);
@@ -352,9 +358,9 @@ int encode_poly(Ctx* ctx, const fe* evals_dev, size_t n, fe** code_out, cudaStre
     MLB_TRY(mobius_launch(evals_dev, coeffs.as<fe>(), n, true, s));
     MLB_TRY(bit_reverse_launch(coeffs.p, rev.p, n, 16, s));
     fe* code;
-    MLB_CUDA(cudaMalloc((void**)&code, (n << ML_LOG_BLOWUP) * 16));
+    MLB_TRY(pmalloc((void**)&code, (n << ML_LOG_BLOWUP) * 16, s));
     int st = ntt_launch(ctx, rev.as<fe>(), code, log_domain, false, true, s);
-    if (st != ML_OK) { cudaFree(code); return st; }
+    if (st != ML_OK) { pfree(code, s); return st; }
     *code_out = code;
     return ML_OK;
 }
@@ -505,10 +511,11 @@ struct BatchedFri {
     ml_merkle* batch_layer = nullptr;
     hfe fingerprint_r = 0;
     ml_fri* fri = nullptr;
+    cudaStream_t stream = nullptr;
     ~BatchedFri() {
         if (owns_codes)
-            for (fe* c : codes) cudaFree(c);
-        if (codes_ptrs_dev) cudaFree(codes_ptrs_dev);
+            for (fe* c : codes) pfree(c, stream);
+        pfree(codes_ptrs_dev, stream);
         if (batch_layer) { batch_layer->owns_data = false; free_merkle(batch_layer); }
         free_fri(fri);
     }
@@ -518,9 +525,10 @@ int bfri_init(BatchedFri* b, ml_transcript* t, cudaStream_t s) {
     const size_t B = b->codes.size(), n = b->n;
     if (B == 0) { set_error("Codes must not be empty"); return ML_ERR_SIZE; }
     MLB_TRY(check_code_len(n));
-    MLB_CUDA(cudaMalloc((void**)&b->codes_ptrs_dev, B * sizeof(fe*)));
+    b->stream = s;
+    MLB_TRY(pmalloc((void**)&b->codes_ptrs_dev, B * sizeof(fe*), s));
     MLB_TRY(h2d(b->codes_ptrs_dev, b->codes.data(), B * sizeof(fe*), s));
-    MLB_TRY(new_merkle(n / 2, &b->batch_layer));
+    MLB_TRY(new_merkle(n / 2, s, &b->batch_layer));
     b->batch_layer->kind = ml_merkle::RS_CODE;
     b->batch_layer->item_bytes = 32;
     b->batch_layer->n_batches = B;
@@ -533,6 +541,7 @@ int bfri_init(BatchedFri* b, ml_transcript* t, cudaStream_t s) {
     absorb_fe(t, b->fingerprint_r);           // :86
     b->fri = new ml_fri();                    // :89-92
     b->fri->log_n0 = (int)ilog2(n);
+    b->fri->stream = s;
     return ML_OK;
 }
 // batched_fold_step (batched_fri.rs:101-181)
@@ -541,9 +550,9 @@ int bfri_batched_fold_step(Ctx* ctx, BatchedFri* b, hfe r, ml_transcript* t, cud
     if (n <= ((size_t)1 << ML_LOG_BLOWUP)) return ML_OK;
     const size_t half_n = n >> 1;
     fe* next;
-    MLB_CUDA(cudaMalloc((void**)&next, half_n * 16));
+    MLB_TRY(pmalloc((void**)&next, half_n * 16, s));
     int st = fri_batched_fold_launch(ctx, b->codes_ptrs_dev, b->codes.size(), n, next, b->fingerprint_r, r, b->fri->log_n0, s);
-    if (st != ML_OK) { cudaFree(next); return st; }
+    if (st != ML_OK) { pfree(next, s); return st; }
     return fold_finish(b->fri, next, half_n, t, s);
 }
 // query phase of BatchedFriProof::prove / BatchedPCSProof::prove (batched_fri.rs:207-225, 296-308)
@@ -650,14 +659,14 @@ int ml_merkle_batch_commit(const uint8_t* const* data, size_t n_batches, size_t 
     if (!is_pow2(n_items)) { set_error("Data length must be a power of two"); return ML_ERR_NOT_POW2; }
     cudaStream_t s = ctx->stream;
     ml_merkle* m;
-    MLB_TRY(new_merkle(n_items, &m));
+    MLB_TRY(new_merkle(n_items, s, &m));
     m->kind = ml_merkle::BYTES;
     m->item_bytes = item_bytes;
     m->n_batches = n_batches;
     int st = ML_OK;
     for (size_t b = 0; b < n_batches && st == ML_OK; b++) {
         void* d = nullptr;
-        if (cudaMalloc(&d, n_items * item_bytes + 16) != cudaSuccess) { set_error("data allocation failed"); st = ML_ERR_ALLOC; break; }
+        if (pmalloc(&d, n_items * item_bytes + 16, s) != ML_OK) { st = ML_ERR_ALLOC; break; }
         m->data.push_back(d);
         st = h2d(d, data[b], n_items * item_bytes, s);
     }
@@ -674,7 +683,7 @@ int ml_merkle_commit_rs_code_dev(const void* code_dev, size_t n, void* stream, m
     MLB_TRY(check_code_len(n));
     cudaStream_t s = ST(stream);
     ml_merkle* m;
-    MLB_TRY(new_merkle(n / 2, &m));
+    MLB_TRY(new_merkle(n / 2, s, &m));
     m->kind = ml_merkle::RS_CODE;
     m->item_bytes = 32;
     m->data.push_back((void*)code_dev);
@@ -744,7 +753,7 @@ int ml_fri_init_dev(const void* code_dev, size_t n, ml_transcript* t, void* stre
     MLB_TRY(check_code_len(n));
     cudaStream_t s = ST(stream);
     fe* code;
-    MLB_CUDA(cudaMalloc((void**)&code, n * 16));
+    MLB_TRY(pmalloc((void**)&code, n * 16, s));
     MLB_CUDA(cudaMemcpyAsync(code, code_dev, n * 16, cudaMemcpyDeviceToDevice, s));
     return fri_init_owned(out, code, n, true, t, s);
 }
@@ -753,7 +762,7 @@ int ml_fri_init(const uint8_t* code_host, size_t n, ml_transcript* t, ml_fri** o
     MLB_TRY(check_code_len(n));
     cudaStream_t s = ctx->stream;
     fe* code;
-    MLB_CUDA(cudaMalloc((void**)&code, n * 16));
+    MLB_TRY(pmalloc((void**)&code, n * 16, s));
     MLB_CUDA(cudaMemcpyAsync(code, code_host, n * 16, cudaMemcpyHostToDevice, s));
     return fri_init_owned(out, code, n, true, t, s);
 }
@@ -873,9 +882,9 @@ static int rs_encode_owned(Ctx* ctx, const void* coeffs_dev, size_t n, fe** code
     const size_t N = n << ML_LOG_BLOWUP;
     MLB_TRY(check_code_len(N));
     fe* code;
-    MLB_CUDA(cudaMalloc((void**)&code, N * 16));
+    MLB_TRY(pmalloc((void**)&code, N * 16, s));
     int st = ntt_launch(ctx, (const fe*)coeffs_dev, code, (int)ilog2(N), false, true, s);
-    if (st != ML_OK) { cudaFree(code); return st; }
+    if (st != ML_OK) { pfree(code, s); return st; }
     *code_out = code;
     return ML_OK;
 }
@@ -1086,7 +1095,8 @@ int ml_batched_fri_prove(const uint8_t* const* codes, size_t n_codes, size_t n, 
     b.n = n;
     for (size_t j = 0; j < n_codes; j++) {
         fe* c;
-        MLB_CUDA(cudaMalloc((void**)&c, n * 16));
+        b.stream = s;
+        MLB_TRY(pmalloc((void**)&c, n * 16, s));
         b.codes.push_back(c);
         MLB_TRY(h2d(c, codes[j], n * 16, s));
     }
@@ -1140,6 +1150,7 @@ int ml_batched_pcs_prove_dev(const uint8_t* inputs, size_t n_vars, const uint8_t
     const size_t domain = n << ML_LOG_BLOWUP;  // batched_pcs.rs:136
     BatchedFri b;
     b.n = domain;
+    b.stream = s;
     for (size_t j = 0; j < n_polys; j++) {  // :144-149
         fe* code;
         MLB_TRY(encode_poly(ctx, (const fe*)evals_dev[j], n, &code, s));
@@ -1153,9 +1164,10 @@ int ml_batched_pcs_prove_dev(const uint8_t* inputs, size_t n_vars, const uint8_t
     // fingerprinted evaluation table (:55-63) straight into the sumcheck matrix
     ml_sumcheck* sc = new ml_sumcheck();
     sc->height = n;
+    sc->stream = s;
     Scratch dptrs(s);
     int st = ML_OK;
-    if (cudaMalloc((void**)&sc->matrix, n * 16) != cudaSuccess || cudaMalloc((void**)&sc->delta, n * 16) != cudaSuccess) { set_error("allocation failed"); st = ML_ERR_ALLOC; }
+    if (pmalloc((void**)&sc->matrix, n * 16, s) != ML_OK || pmalloc((void**)&sc->delta, n * 16, s) != ML_OK) st = ML_ERR_ALLOC;
     if (st == ML_OK) st = dptrs.alloc(n_polys * sizeof(void*));
     if (st == ML_OK) st = h2d(dptrs.p, evals_dev, n_polys * sizeof(void*), s);
     if (st == ML_OK) st = fingerprint_rows_launch((const fe* const*)dptrs.p, n_polys, n, fr, sc->matrix, s);
@@ -1190,13 +1202,12 @@ int ml_batched_pcs_prove(const uint8_t* inputs, size_t n_vars, const uint8_t* ou
     std::vector<void*> dev(n_polys, nullptr);
     int st = ML_OK;
     for (size_t j = 0; j < n_polys && st == ML_OK; j++) {
-        if (cudaMalloc(&dev[j], n * 16 + 16) != cudaSuccess) { set_error("allocation failed"); st = ML_ERR_ALLOC; break; }
+        if (pmalloc(&dev[j], n * 16 + 16, s) != ML_OK) { st = ML_ERR_ALLOC; break; }
         st = h2d(dev[j], evals[j], n * 16, s);
     }
     if (st == ML_OK) st = ml_batched_pcs_prove_dev(inputs, n_vars, outputs, n_polys, dev.data(), n, t, s, out);
     cudaStreamSynchronize(s);
-    for (void* d : dev)
-        if (d) cudaFree(d);
+    for (void* d : dev) pfree(d, s);
     return st;
 }
 int ml_batched_pcs_verify(const ml_bpcs_proof* p, ml_transcript* t) {  // batched_pcs.rs:182-253

@@ -96,6 +96,7 @@ int sumcheck_sums_launch(Ctx* ctx, const fe* m, const fe* d, size_t height, hfe*
     const unsigned nb = blocks_for(off);
     fe* partials;
     MLB_TRY(dev_alloc_async((void**)&partials, (size_t)(2 * nb + 2) * 16, s));
+    ProfScope prof(PROF_SUMCHECK_SUMS, 32.0 * (double)height, s);  // read both tables once
     sumcheck_sums_kernel<<<nb, SC_THREADS, 0, s>>>(m, d, off, partials);
     MLB_KERNEL_CHECK();
     reduce_partials_kernel<<<1, 256, 0, s>>>(partials, (int)nb, 2, partials + 2 * nb);
@@ -124,6 +125,7 @@ int sumcheck_partial_sum_launch(Ctx* ctx, const fe* m, const fe* d, size_t heigh
 int sumcheck_fold_launch(fe* m, fe* d, size_t height, hfe r, cudaStream_t s) {
     const size_t off = height >> 1;
     if (off == 0) return ML_OK;
+    ProfScope prof(PROF_SUMCHECK_FOLD, 48.0 * (double)height, s);  // read 2 tables (h), write 2 half tables
     sumcheck_fold_kernel<<<blocks_for(off), 256, 0, s>>>(m, d, off, to_dev_fe_h(r));
     MLB_KERNEL_CHECK();
     return ML_OK;
