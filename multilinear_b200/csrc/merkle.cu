@@ -21,24 +21,60 @@ __device__ __forceinline__ uint8_t* layer_ptr(uint8_t* digests, size_t n_leaves,
     return digests + 32 * ((2 * n_leaves - ((2 * n_leaves) >> layer)) + idx);
 }
 
-// Push digest h of node `idx` at `layer` up a thread-private stack; j = index within the thread's group.
-template <int LOG_G>
-__device__ __forceinline__ void subtree_push(uint32_t (&stack)[LOG_G > 0 ? LOG_G : 1][8], uint32_t h[8], int j, uint8_t* digests,
-                                             size_t n_leaves, int base_layer, size_t idx) {
-#pragma unroll
-    for (int lvl = 0; lvl < LOG_G; lvl++) {
-        if ((j >> lvl) & 1) {
-            uint32_t o[8];
-            sha256_node64(stack[lvl], h, o);
-#pragma unroll
-            for (int w = 0; w < 8; w++) h[w] = o[w];
-            idx >>= 1;
-            sha_store_digest(layer_ptr(digests, n_leaves, base_layer + lvl + 1, idx), h);
+// Thread-private subtree walk.  A thread owns 2^G consecutive nodes of `base_layer` (leaves when LEAVES) and computes
+// the G layers above them with a G-deep digest stack.  The walk is written as ONE loop whose body holds a single
+// inlined copy of the compression function (37 KB of straight-line SASS): unrolling the 2^(G+1)-1 hashes instead
+// makes a ~450 KB body that thrashes the instruction cache (ncu: stall_no_instruction dominant, profiles/r1_*).
+// Control flow depends only on (j, lvl), identical for every thread, so there is no divergence; the stack is
+// indexed dynamically and lives in local memory (32 bytes of traffic per 2400-instruction hash).
+template <int LOG_G, bool LEAVES>
+__device__ __forceinline__ void subtree_walk(const fe* __restrict__ code, uint8_t* __restrict__ digests, size_t n_leaves, int base_layer,
+                                             size_t first) {
+    uint32_t stack[LOG_G > 0 ? LOG_G : 1][8];
+    uint32_t h[8];
+    int j = 0, lvl = -1;  // lvl < 0: next hash is leaf j; otherwise node(stack[lvl], h)
+    size_t idx = first;
+#pragma unroll 1
+    while (j < (1 << LOG_G)) {
+        uint32_t w[16], st[8];
+        const bool leaf = lvl < 0;
+        if (leaf) {
+            idx = first + j;
+            if (LEAVES) {
+                sha_words_from_le(__ldg(reinterpret_cast<const uint4*>(code + idx)), w);
+                sha_words_from_le(__ldg(reinterpret_cast<const uint4*>(code + idx + n_leaves)), w + 4);
+                w[8] = 0x80000000u; w[9] = 0; w[10] = 0; w[11] = 0; w[12] = 0; w[13] = 0; w[14] = 0; w[15] = 256u;
+            } else {
+                sha_load_digest(layer_ptr(digests, n_leaves, base_layer, idx), h);
+            }
         } else {
 #pragma unroll
-            for (int w = 0; w < 8; w++) stack[lvl][w] = h[w];
-            break;
+            for (int k = 0; k < 8; k++) { w[k] = stack[lvl][k]; w[8 + k] = h[k]; }
         }
+        if (LEAVES || !leaf) {
+            sha_iv(st);
+            sha_compress(st, w);
+            if (!leaf) {
+                uint32_t p[16] = {0x80000000u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 512u};
+                sha_compress(st, p);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) h[k] = st[k];
+            if (leaf) {
+                sha_store_digest(layer_ptr(digests, n_leaves, base_layer, idx), h);
+            } else {
+                idx >>= 1;
+                sha_store_digest(layer_ptr(digests, n_leaves, base_layer + lvl + 1, idx), h);
+            }
+        }
+        lvl = leaf ? 0 : lvl + 1;
+        if (lvl < LOG_G && ((j >> lvl) & 1)) continue;  // left sibling is waiting on the stack: hash the parent next
+        if (lvl < LOG_G) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) stack[lvl][k] = h[k];
+        }
+        j++;
+        lvl = -1;
     }
 }
 
@@ -47,17 +83,7 @@ template <int LOG_G>
 __global__ void __launch_bounds__(128) merkle_rs_kernel(const fe* __restrict__ code, size_t n_leaves, uint8_t* __restrict__ digests) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if ((g << LOG_G) >= n_leaves) return;
-    uint32_t stack[LOG_G > 0 ? LOG_G : 1][8];
-#pragma unroll
-    for (int j = 0; j < (1 << LOG_G); j++) {
-        const size_t i = (g << LOG_G) + j;
-        uint32_t m[8], h[8];
-        sha_words_from_le(__ldg(reinterpret_cast<const uint4*>(code + i)), m);
-        sha_words_from_le(__ldg(reinterpret_cast<const uint4*>(code + i + n_leaves)), m + 4);
-        sha256_leaf32(m, h);
-        sha_store_digest(layer_ptr(digests, n_leaves, 0, i), h);
-        subtree_push<LOG_G>(stack, h, j, digests, n_leaves, 0, i);
-    }
+    subtree_walk<LOG_G, true>(code, digests, n_leaves, 0, g << LOG_G);
 }
 
 // Thread g reads 2^G consecutive digests of `from_layer` and writes the G layers above them.
@@ -66,14 +92,7 @@ __global__ void __launch_bounds__(128) merkle_nodes_kernel(uint8_t* __restrict__
     const size_t count = n_leaves >> from_layer;
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if ((g << LOG_G) >= count) return;
-    uint32_t stack[LOG_G > 0 ? LOG_G : 1][8];
-#pragma unroll
-    for (int j = 0; j < (1 << LOG_G); j++) {
-        const size_t i = (g << LOG_G) + j;
-        uint32_t h[8];
-        sha_load_digest(layer_ptr(digests, n_leaves, from_layer, i), h);
-        subtree_push<LOG_G>(stack, h, j, digests, n_leaves, from_layer, i);
-    }
+    subtree_walk<LOG_G, false>(nullptr, digests, n_leaves, from_layer, g << LOG_G);
 }
 
 // One CTA finishes the tree from a layer with <= 2 * blockDim.x * 4 nodes (loops otherwise).
