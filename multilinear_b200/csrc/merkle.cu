@@ -54,10 +54,7 @@ __device__ __forceinline__ void subtree_walk(const fe* __restrict__ code, uint8_
         if (LEAVES || !leaf) {
             sha_iv(st);
             sha_compress(st, w);
-            if (!leaf) {
-                uint32_t p[16] = {0x80000000u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 512u};
-                sha_compress(st, p);
-            }
+            if (!leaf) sha_compress_pad512(st);
 #pragma unroll
             for (int k = 0; k < 8; k++) h[k] = st[k];
             if (leaf) {

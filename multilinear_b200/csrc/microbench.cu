@@ -4,6 +4,7 @@
 #include "field.cuh"
 #include "internal.h"
 #include "sha256.cuh"
+#include <cstdlib>
 #include <string>
 
 namespace mlb {
@@ -30,7 +31,7 @@ __global__ void __launch_bounds__(256) mb_field_kernel(fe* out, int iters, fe se
     fe r = fe_add(fe_add(a[0], a[1]), fe_add(a[2], a[3]));
     if (r.v[0] == 0x12345678u && r.v[3] == 0x9abcdef0u) fe_store(out + tid, r);  // keep the chain live
 }
-template <int MODE>  // 0: 32-byte leaf hash, 1: 64-byte node hash
+template <int MODE, int FMA_ADD>  // 0: 32-byte leaf hash, 1: 64-byte node hash; FMA_ADD = add-routing mask
 __global__ void __launch_bounds__(128) mb_sha_kernel(uint32_t* out, int iters, uint32_t seed) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t h[8], g[8];
@@ -38,13 +39,46 @@ __global__ void __launch_bounds__(128) mb_sha_kernel(uint32_t* out, int iters, u
     for (int i = 0; i < 8; i++) { h[i] = seed + tid * 8 + i; g[i] = seed ^ (tid + i); }
     for (int it = 0; it < iters; it++) {
         uint32_t o[8];
-        if (MODE == 0) sha256_leaf32(h, o);
-        else sha256_node64(h, g, o);
+        sha_iv(o);
+        if (MODE == 0) {
+            uint32_t w[16] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], 0x80000000u, 0u, 0u, 0u, 0u, 0u, 0u, 256u};
+            sha_compress_t<FMA_ADD>(o, w);
+        } else {
+            uint32_t w[16] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7]};
+            sha_compress_t<FMA_ADD>(o, w);
+            sha_compress_pad512_t<FMA_ADD>(o);
+        }
 #pragma unroll
         for (int i = 0; i < 8; i++) h[i] = o[i];
     }
     if (h[0] == 0x12345678u && h[7] == 0x9abcdef0u) out[tid] = h[3];
 }
+// raw pipe throughput: MODE 0 IADD3, 1 IMAD (32-bit), 2 IMAD.WIDE, 3 SHF (funnel shift), 4 LOP3, 5 IADD3+IMAD 1:1,
+// 6 SHF+IMAD 1:1, 7 SHF+IMAD.WIDE 1:1, 8 SHF+LOP3 1:1, 9 SHF+LOP3+IMAD 1:1:1
+template <int MODE>
+__global__ void __launch_bounds__(256) mb_pipe_kernel(uint32_t* out, int iters, uint32_t seed) {
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t a[8], b[8];
+    unsigned long long wd[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a[i] = seed + tid * 8 + i; b[i] = seed ^ (tid + 77 * i); wd[i] = a[i]; }
+    uint32_t m = seed | 1u;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (MODE == 0 || MODE == 5) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i]));
+            if (MODE == 1 || MODE == 5 || MODE == 6 || MODE == 9) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(b[i]) : "r"(m), "r"(a[i]));
+            if (MODE == 2 || MODE == 7) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(wd[i]) : "r"(b[i]), "r"(m));
+            if (MODE == 3 || MODE == 6 || MODE == 7 || MODE == 8 || MODE == 9) asm volatile("shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(a[i]));
+            if (MODE == 4 || MODE == 8 || MODE == 9) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[i]) : "r"(a[i]), "r"(m));
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r += a[i] + b[i] + (uint32_t)wd[i] + (uint32_t)(wd[i] >> 32);
+    if (r == 0x12345678u) out[tid] = r;
+}
+
 __global__ void __launch_bounds__(256) mb_copy_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -75,8 +109,29 @@ extern "C" int ml_microbench(const char* what, size_t n, int iters, double* ms_o
         MLB_CUDA(cudaEventRecord(e0, s));
         if (w == "modmul") mb_field_kernel<0><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((fe*)buf, iters, seed);
         else if (w == "butterfly") mb_field_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((fe*)buf, iters, seed);
-        else if (w == "sha_leaf") mb_sha_kernel<0><<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t*)buf, iters, 0x1234567u);
-        else if (w == "sha_node") mb_sha_kernel<1><<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t*)buf, iters, 0x1234567u);
+        else if (w == "sha_leaf") mb_sha_kernel<0, MLB_SHA_ADD_MASK><<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t*)buf, iters, 0x1234567u);
+        else if (w == "sha_node") mb_sha_kernel<1, MLB_SHA_ADD_MASK><<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t*)buf, iters, 0x1234567u);
+#define MB_SHA_VARIANT(M)                                                                                                              \
+        else if (w == "sha_leaf_m" #M) mb_sha_kernel<0, M><<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); \
+        else if (w == "sha_node_m" #M) mb_sha_kernel<1, M><<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t*)buf, iters, 0x1234567u);
+        MB_SHA_VARIANT(0) MB_SHA_VARIANT(63) MB_SHA_VARIANT(3) MB_SHA_VARIANT(1) MB_SHA_VARIANT(2) MB_SHA_VARIANT(19) MB_SHA_VARIANT(11)
+        MB_SHA_VARIANT(27) MB_SHA_VARIANT(59) MB_SHA_VARIANT(43)
+        else if (w.rfind("pipe", 0) == 0) {
+            const int mode = atoi(what + 4);
+            const unsigned gb = (unsigned)((n + 255) / 256);
+            switch (mode) {
+                case 0: mb_pipe_kernel<0><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
+                case 1: mb_pipe_kernel<1><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
+                case 2: mb_pipe_kernel<2><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
+                case 3: mb_pipe_kernel<3><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
+                case 4: mb_pipe_kernel<4><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
+                case 5: mb_pipe_kernel<5><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
+                case 6: mb_pipe_kernel<6><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
+                case 7: mb_pipe_kernel<7><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
+                case 8: mb_pipe_kernel<8><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
+                default: mb_pipe_kernel<9><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
+            }
+        }
         else if (w == "copy") mb_copy_kernel<<<148 * 16, 256, 0, s>>>((const uint4*)buf, (uint4*)((uint8_t*)buf + n), n / 16);
         else { cudaFree(buf); set_error("ml_microbench: unknown benchmark '%s'", what); return ML_ERR_ARG; }
         MLB_KERNEL_CHECK();
@@ -93,6 +148,11 @@ extern "C" int ml_microbench(const char* what, size_t n, int iters, double* ms_o
     if (w == "modmul") *work_out = (double)n * iters * 4;
     else if (w == "butterfly") *work_out = (double)n * iters * 2;
     else if (w == "copy") *work_out = 2.0 * (double)n;
+    else if (w.rfind("pipe", 0) == 0) {
+        const int mode = atoi(what + 4);
+        const int per = mode <= 4 ? 1 : (mode == 9 ? 3 : 2);
+        *work_out = (double)n * iters * 8 * per;  // thread-instructions
+    }
     else *work_out = (double)n * iters;
     return ML_OK;
 }

@@ -51,18 +51,75 @@ __device__ __forceinline__ void sha_iv(uint32_t st[8]) {
     st[4] = MLB_SHA_IV4; st[5] = MLB_SHA_IV5; st[6] = MLB_SHA_IV6; st[7] = MLB_SHA_IV7;
 }
 
+// Additions can be routed to the fma pipe.  SHA-256 is bound by the alu pipe (rotates = SHF, boolean functions =
+// LOP3, about 1.0k such instructions per compression, 2 cycles each per SM sub-partition).  `x * 1 + y` with the 1
+// read from the constant bank cannot be folded, so it is emitted as IMAD on the fma pipe.
+// MASK bit set -> that group of additions is emitted as IMAD; clear -> left to ptxas (IADD3 / IMAD.IADD mix):
+//   1 message schedule, 2 h + K + W, 4 t1 (+ch, +S1), 8 t2 = S0 + maj, 16 e = d + t1, 32 a = t1 + t2
+// Measured on B200 (tools/shabench.py, profiles/r1_sha_add_routing.txt); the default is the fastest mix.
+__constant__ uint32_t kShaOne = 1u;
+template <bool FMA_ADD>
+__device__ __forceinline__ uint32_t sha_add(uint32_t a, uint32_t b) {
+    return FMA_ADD ? a * kShaOne + b : a + b;
+}
+#ifndef MLB_SHA_ADD_MASK
+#define MLB_SHA_ADD_MASK 2
+#endif
+
 // One compression; w[16] holds the block as big-endian words and is clobbered (rolling schedule).
-__device__ __forceinline__ void sha_compress(uint32_t st[8], uint32_t w[16]) {
+template <int MASK>
+__device__ __forceinline__ void sha_compress_t(uint32_t st[8], uint32_t w[16]) {
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll
     for (int i = 0; i < 64; i++) {
-        if (i >= 16) w[i & 15] = w[i & 15] + sha_s0(w[(i + 1) & 15]) + w[(i + 9) & 15] + sha_s1(w[(i + 14) & 15]);
-        uint32_t t1 = h + sha_S1(e) + sha_ch(e, f, g) + kShaK[i] + w[i & 15];
-        uint32_t t2 = sha_S0(a) + sha_maj(a, b, c);
-        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        if (i >= 16)
+            w[i & 15] = sha_add<(MASK & 1) != 0>(sha_add<(MASK & 1) != 0>(w[i & 15], sha_s0(w[(i + 1) & 15])),
+                                                 sha_add<(MASK & 1) != 0>(w[(i + 9) & 15], sha_s1(w[(i + 14) & 15])));
+        // h + K + W first: it does not depend on this round's e, so it stays off the critical path
+        uint32_t hkw = sha_add<(MASK & 2) != 0>(sha_add<(MASK & 2) != 0>(w[i & 15], kShaK[i]), h);
+        uint32_t t1 = sha_add<(MASK & 4) != 0>(sha_add<(MASK & 4) != 0>(hkw, sha_ch(e, f, g)), sha_S1(e));
+        uint32_t t2 = sha_add<(MASK & 8) != 0>(sha_S0(a), sha_maj(a, b, c));
+        h = g; g = f; f = e; e = sha_add<(MASK & 16) != 0>(d, t1); d = c; c = b; b = a; a = sha_add<(MASK & 32) != 0>(t1, t2);
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
+__device__ __forceinline__ void sha_compress(uint32_t st[8], uint32_t w[16]) { sha_compress_t<MLB_SHA_ADD_MASK>(st, w); }
+
+// Compression over a constant block (the padding block that ends every 64-byte message): the whole message
+// schedule is known at compile time, so round i only needs the immediate K[i] + W[i].
+struct ShaKW {
+    uint32_t v[64];
+};
+constexpr uint32_t sha_rotr_c(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+constexpr ShaKW sha_make_pad_kw(uint32_t message_bits) {
+    constexpr uint32_t K[64] = {MLB_SHA_K_LIST};
+    uint32_t w[64] = {};
+    w[0] = 0x80000000u;
+    w[15] = message_bits;
+    for (int i = 16; i < 64; i++) {
+        uint32_t s0 = sha_rotr_c(w[i - 15], 7) ^ sha_rotr_c(w[i - 15], 18) ^ (w[i - 15] >> 3);
+        uint32_t s1 = sha_rotr_c(w[i - 2], 17) ^ sha_rotr_c(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    ShaKW r = {};
+    for (int i = 0; i < 64; i++) r.v[i] = K[i] + w[i];
+    return r;
+}
+__device__ static constexpr ShaKW kShaPad512 = sha_make_pad_kw(512u);
+
+template <int MASK>
+__device__ __forceinline__ void sha_compress_pad512_t(uint32_t st[8]) {
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        uint32_t hkw = sha_add<(MASK & 2) != 0>(h, kShaPad512.v[i]);
+        uint32_t t1 = sha_add<(MASK & 4) != 0>(sha_add<(MASK & 4) != 0>(hkw, sha_ch(e, f, g)), sha_S1(e));
+        uint32_t t2 = sha_add<(MASK & 8) != 0>(sha_S0(a), sha_maj(a, b, c));
+        h = g; g = f; f = e; e = sha_add<(MASK & 16) != 0>(d, t1); d = c; c = b; b = a; a = sha_add<(MASK & 32) != 0>(t1, t2);
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+__device__ __forceinline__ void sha_compress_pad512(uint32_t st[8]) { sha_compress_pad512_t<MLB_SHA_ADD_MASK>(st); }
 
 // SHA-256 of a 32-byte message given as 8 big-endian words.
 __device__ __forceinline__ void sha256_leaf32(const uint32_t m[8], uint32_t out[8]) {
@@ -76,8 +133,7 @@ __device__ __forceinline__ void sha256_node64(const uint32_t l[8], const uint32_
     uint32_t w[16] = {l[0], l[1], l[2], l[3], l[4], l[5], l[6], l[7], r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]};
     sha_iv(out);
     sha_compress(out, w);
-    uint32_t p[16] = {0x80000000u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 512u};
-    sha_compress(out, p);  // constant block: the whole schedule constant-folds
+    sha_compress_pad512(out);  // constant padding block: schedule folded into immediates
 }
 
 // Field element (LE limbs as stored) -> the 4 big-endian message words of its 16 bytes.
