@@ -27,10 +27,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
+DRAM_TRAFFIC = {}
 METRIC = "pcs_commit_melem_per_s"
 UNIT = "Melem/s"
 PROF_NAMES = ["ntt_rs_encode", "merkle_leaf_subtree", "merkle_nodes", "merkle_top", "fri_fold", "sumcheck_sums", "sumcheck_fold",
-              "mobius", "eq_table", "bit_reverse", "query_gather"]
+              "mobius", "eq_table", "bit_reverse", "query_gather", "fused_tail", "transcript_step"]
 
 
 def env_int(name, default):
@@ -156,15 +158,40 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n = 1 << args.log_n
-    N = 2 * n
-    coeffs = ml.synthetic_elements_dev(0xB200 + rank, n)  # resident in HBM before the timed region
+    P = max(1, args.polys_per_gpu)
+    # P independent polynomials per GPU, resident in HBM before the timed region; each is committed on its own
+    # stream by its own host thread so the latency-bound phases of one commit (tree tops, fused tail, transcript
+    # steps) overlap the throughput-bound kernels of the others
+    coeffs = [ml.synthetic_elements_dev(0xB200 + rank * 64 + j, n) for j in range(P)]
+    streams = []
+    for _ in range(P):
+        h = C.c_void_p()
+        ml.check(L.ml_stream_create(C.byref(h)))
+        streams.append(h)
     ml.synchronize()
+    results = [None] * P
 
-    def step():
-        f = ml.FriProverData.fold_from_coeffs_dev(coeffs, n, ml.Transcript(), None)
-        roots, last = f.fold_roots(), f.last_element
+    def commit(j):
+        f = ml.FriProverData.fold_from_coeffs_dev(coeffs[j], n, ml.Transcript(), streams[j].value)
+        out = (f.fold_roots(), f.last_element)
         del f  # the handle (all layers, ~3.5 GB at 2^24) returns to the stream-ordered pool
-        return roots, last
+        return out
+
+    def worker(j, steps):
+        ml.set_device(local_rank)  # the CUDA current device is per host thread
+        for _ in range(steps):
+            results[j] = commit(j)
+
+    def run_steps(steps, which=None):
+        js = list(range(P)) if which is None else which
+        if len(js) == 1:
+            worker(js[0], steps)
+            return
+        ts = [threading.Thread(target=worker, args=(j, steps)) for j in js]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
 
     def barrier():
         torch.cuda.synchronize()
@@ -173,59 +200,87 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     L.ml_profile_enable(0)
-    for _ in range(args.warmup):
-        roots, last = step()
-    L.ml_profile_reset()
-    L.ml_profile_enable(1)
+    run_steps(args.warmup)
     sampler = ClockSampler(local_rank)
     barrier()
     launches0 = ml.kernel_launches()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        roots, last = step()
+    e0.record()  # legacy default stream: ordered against the (blocking) worker streams
+    run_steps(args.steps)
     e1.record()
     barrier()
     sampler.stop_flag = True
     ms = e0.elapsed_time(e1) / args.steps
     launches = ml.kernel_launches() - launches0
-    L.ml_profile_enable(0)
+    roots, last = results[0]
 
-    # per-kernel device time inside the timed region
+    # ---- serial pass of the same workload (one commit at a time) with per-kernel CUDA-event timing: per-kernel
+    # durations are only well defined when commits do not share the GPU
+    ser_steps = max(2, min(args.steps, 5))
+    L.ml_profile_reset()
+    L.ml_profile_enable(1)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    run_steps(ser_steps, which=[0])
+    s1.record()
+    barrier()
+    ms_serial = s0.elapsed_time(s1) / ser_steps
+    L.ml_profile_enable(0)
     kernels = {}
     for i, name in enumerate(PROF_NAMES):
         t, cnt, by = C.c_double(0), C.c_uint64(0), C.c_double(0)
         L.ml_profile_get(C.c_int(i), C.byref(t), C.byref(cnt), C.byref(by))
         if cnt.value:
-            kernels[name] = {"ms_per_step": t.value / args.steps, "launches_per_step": cnt.value / args.steps,
-                             "alg_bytes_per_step": by.value / args.steps,
+            kernels[name] = {"ms_per_commit": t.value / ser_steps, "launches_per_commit": cnt.value / ser_steps,
+                             "alg_bytes_per_commit": by.value / ser_steps,
                              "achieved_gbs": by.value / (t.value * 1e-3) / 1e9 if t.value > 0 else None}
     L.ml_profile_reset()
 
-    # ---- e2e through the host-pointer C ABI (pinned host input, proof back on the host)
+    # ---- e2e through the host-pointer C ABI (pinned host input, proof back on the host), same P-way pipelining
     e2e_steps = max(1, min(args.steps, 5))
-    pinned = C.c_void_p()
-    ml.check(L.ml_host_alloc_pinned(C.c_size_t(16 * n), C.byref(pinned)))
-    ml.check(L.ml_dev_download(pinned, coeffs.ptr, C.c_size_t(16 * n)))
-
-    def e2e_step():
-        t = ml.Transcript()
+    PE = max(1, args.e2e_polys)
+    while len(streams) < PE:
         h = C.c_void_p()
-        ml.check(L.ml_rs_fri_prove(pinned, C.c_size_t(n), t.h, C.byref(h)))
-        proof = ml.FriProof(h)
-        blob = proof.serialize()
-        return proof, len(blob)
+        ml.check(L.ml_stream_create(C.byref(h)))
+        streams.append(h)
+    pinned = []
+    for j in range(PE):
+        hp = C.c_void_p()
+        ml.check(L.ml_host_alloc_pinned(C.c_size_t(16 * n), C.byref(hp)))
+        ml.check(L.ml_dev_download(hp, coeffs[j % P].ptr, C.c_size_t(16 * n)))
+        pinned.append(hp)
+    e2e_out = [None] * PE
 
-    proof, blob_len = e2e_step()  # warm-up
+    def e2e_worker(j, steps):
+        ml.set_device(local_rank)
+        ml.check(L.ml_set_thread_stream(streams[j], C.c_int(1)))
+        for _ in range(steps):
+            t = ml.Transcript()
+            h = C.c_void_p()
+            ml.check(L.ml_rs_fri_prove(pinned[j], C.c_size_t(n), t.h, C.byref(h)))
+            proof = ml.FriProof(h)
+            e2e_out[j] = (proof.commitments, proof.last_elem, len(proof.serialize()))
+            del proof
+
+    def e2e_run(steps):
+        ts = [threading.Thread(target=e2e_worker, args=(j, steps)) for j in range(PE)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    e2e_run(1)  # warm-up
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        proof, blob_len = e2e_step()
+    e2e_run(e2e_steps)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    e2e_ok = proof.commitments == roots and proof.last_elem == last
-    L.ml_host_free_pinned(pinned)
+    blob_len = e2e_out[0][2]
+    e2e_ok = e2e_out[0][0] == roots and e2e_out[0][1] == last
+    for hp in pinned:
+        L.ml_host_free_pinned(hp)
 
     # max over ranks
     if dist is not None:
@@ -237,7 +292,7 @@ def run_ours(args):
         launches = int(ll[0])
 
     if rank == 0:
-        value = world * n / (ms * 1e-3) / 1e6
+        value = world * P * n / (ms * 1e-3) / 1e6
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -245,21 +300,23 @@ def run_ours(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-        dom = max(kernels.items(), key=lambda kv: kv[1]["ms_per_step"]) if kernels else (None, None)
+        dom = max(kernels.items(), key=lambda kv: kv[1]["ms_per_commit"]) if kernels else (None, None)
         roofline = None
         if dom[0]:
             k = dom[1]
-            per_launch_bytes = k["alg_bytes_per_step"] / k["launches_per_step"]
-            per_launch_ms = k["ms_per_step"] / k["launches_per_step"]
+            per_launch_bytes = k["alg_bytes_per_commit"] / k["launches_per_commit"]
+            per_launch_ms = k["ms_per_commit"] / k["launches_per_commit"]
             ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                        "traffic": None, "peak_source": peak_src, "share_of_step": k["ms_per_step"] / ms,
-                        "note": "SHA-256 hashing is integer-pipe (alu) bound, not HBM bound; see int_pipe and profiles/"}
+                        "traffic": DRAM_TRAFFIC.get(dom[0]), "peak_source": peak_src, "share_of_step": k["ms_per_commit"] / ms_serial,
+                        "launches_per_commit": k["launches_per_commit"],
+                        "note": "SHA-256 hashing is integer-pipe (alu) bound, not HBM bound (int_pipe_frac = time at the measured "
+                                "integer speed of light / actual); per-kernel times come from the serial pass of this run"}
         ntt = kernels.get("ntt_rs_encode")
         extra = {}
         if ntt:
             extra["ntt_roofline"] = {"bound": "hbm", "achieved": ntt["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                                     "frac": ntt["achieved_gbs"] / hbm_peak, "alg_bytes": ntt["alg_bytes_per_step"], "ms": ntt["ms_per_step"]}
+                                     "frac": ntt["achieved_gbs"] / hbm_peak, "alg_bytes": ntt["alg_bytes_per_commit"], "ms": ntt["ms_per_commit"]}
         # integer-pipe speed of light measured on this GPU (no HBM traffic)
         try:
             sol = {}
@@ -270,7 +327,7 @@ def run_ours(args):
             if dom[0] == "merkle_leaf_subtree":
                 leaves = 2.0 * n  # sum over the fold chain of leaves handled by the leaf/subtree kernel
                 ideal_ms = (leaves / sol["sha_leaf_per_s"] + leaves * 0.875 / sol["sha_node_per_s"]) * 1e3
-                roofline["int_pipe_frac"] = ideal_ms / dom[1]["ms_per_step"]
+                roofline["int_pipe_frac"] = ideal_ms / dom[1]["ms_per_commit"]
         except Exception as e:  # noqa: BLE001
             extra["int_pipe_error"] = str(e)
 
@@ -286,10 +343,15 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u128", "data": "synthetic",
-            "config": {"workload": "pcs_commit_rs_merkle_fri_fold", "log_n": args.log_n, "blowup": 2, "polys_per_gpu": 1,
-                       "l2": "inputs larger than L2 (256 MiB coefficients, 512 MiB code per step)", "parallelism": "independent commits per GPU"},
+            "config": {"workload": "pcs_commit_rs_merkle_fri_fold", "log_n": args.log_n, "blowup": 2, "polys_per_gpu": P,
+                       "step": "one commit of each of the %d resident polynomials of 2^%d coefficients per GPU" % (P, args.log_n),
+                       "l2": "inputs larger than L2 (256 MiB coefficients, 512 MiB code per commit)",
+                       "parallelism": "independent commits: %d streams per GPU, no data-path collective" % P},
+            "serial": {"ms_per_commit": ms_serial, "value": world * n / (ms_serial * 1e-3) / 1e6, "unit": UNIT,
+                       "note": "one commit at a time on one stream (latency-bound phases exposed)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "e2e": {"value": world * n / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": blob_len,
+            "e2e": {"value": world * PE * n / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 16 * n * PE, "d2h_bytes_per_step": blob_len * PE,
+                    "polys_in_flight": PE,
                     "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "includes": "128 query openings + proof serialisation", "matches_device_run": bool(e2e_ok)},
             "gpu_launches": launches, "clocks": sampler.result(), "kernels": kernels,
         }
@@ -309,6 +371,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=24, dest="log_n")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--polys-per-gpu", type=int, default=2, dest="polys_per_gpu",
+                    help="independent polynomials committed concurrently per GPU (one stream + host thread each)")
+    ap.add_argument("--e2e-polys", type=int, default=4, dest="e2e_polys",
+                    help="concurrent commits in the end-to-end leg (more in flight hides the PCIe copies)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -65,6 +65,14 @@ int ml_synchronize(void);
 /* number of kernels this library has launched in the calling process (bench.py's `gpu_launches`) */
 uint64_t ml_kernel_launches(void);
 
+/* Streams.  Host-pointer entry points run on a per-device library stream unless the calling thread installed its
+ * own with ml_set_thread_stream; `_dev` entry points take the stream explicitly.  Several host threads may drive
+ * independent commits on different streams of one GPU (the library is thread-safe across handles). */
+int ml_stream_create(void **out);
+int ml_stream_destroy(void *stream);
+int ml_stream_synchronize(void *stream);
+int ml_set_thread_stream(void *stream, int enable);
+
 /* raw device memory for callers that keep data resident (bench, multi-GPU orchestration) */
 int ml_dev_alloc(size_t bytes, void **out);
 int ml_dev_free(void *p);
@@ -232,7 +240,7 @@ int ml_merkle_top_from_roots(const uint8_t *roots, size_t n_roots, uint8_t root_
  * ml_profile_*: when enabled, every kernel group is bracketed by CUDA events on its launch stream;
  * ml_profile_get sums device time, launches and algorithmic HBM bytes (input read once + output written once)
  * per group id: 0 ntt_pass, 1 merkle_leaf_subtree, 2 merkle_nodes, 3 merkle_top, 4 fri_fold, 5 sumcheck_sums,
- * 6 sumcheck_fold, 7 mobius, 8 eq_table, 9 bit_reverse, 10 query_gather.
+ * 6 sumcheck_fold, 7 mobius, 8 eq_table, 9 bit_reverse, 10 query_gather, 11 fused_tail, 12 transcript_step.
  * ml_microbench: integer-pipe speed-of-light loops ("modmul", "butterfly", "sha_leaf", "sha_node", "copy"). */
 int ml_profile_enable(int on);
 int ml_profile_reset(void);

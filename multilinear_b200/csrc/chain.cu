@@ -1,0 +1,268 @@
+// Sync-free fold chain: device-resident transcript steps and the fused tail kernel.
+//
+// Reference control flow (src/fri/mod.rs:136-145, src/fri/multilinear_pcs.rs:58-73): per round the prover
+//   [sumcheck: two partial sums -> round polynomial -> absorb c1,c2] -> r = next_challenge() -> fold tables and code
+//   with r -> Merkle-commit the folded code -> absorb its root.
+// Every step depends on the previous one through the transcript.  With the transcript on the host that is one
+// device->host round trip per round (24 at 2^24).  Here:
+//   * large rounds: the same kernels as before, but the challenge is produced by a one-thread kernel that advances
+//     the transcript in HBM and leaves r (and r/2) in device memory for the fold kernels — nothing returns to the host;
+//   * once the code fits one CTA (<= 4096 elements) a single kernel runs ALL remaining rounds: sumcheck sums,
+//     transcript, table fold, FRI fold, leaf hashes, tree levels, in shared/L2 with __syncthreads between phases.
+//     This replaces ~60 latency-bound launches (ncu: 20-220 us each, profiles/r1_launches_bench_v0.csv).
+#include "field.cuh"
+#include "internal.h"
+#include "reduce.cuh"
+#include "sha256.cuh"
+
+namespace mlb {
+// single expansions of the compression function for the whole translation unit (leaf, node and transcript hashing)
+static __device__ __noinline__ void chain_compress(uint32_t st[8], uint32_t w[16]) { sha_compress(st, w); }
+static __device__ __noinline__ void chain_compress_pad512(uint32_t st[8]) { sha_compress_pad512(st); }
+}  // namespace mlb
+#define MLB_DT_COMPRESS(h, w) chain_compress(h, w)
+#include "transcript.cuh"
+
+namespace mlb {
+
+__device__ __forceinline__ void chain_leaf(uint4 x, uint4 y, uint32_t out[8]) {
+    uint32_t w[16];
+    sha_words_from_le(x, w);
+    sha_words_from_le(y, w + 4);
+    w[8] = 0x80000000u; w[9] = 0; w[10] = 0; w[11] = 0; w[12] = 0; w[13] = 0; w[14] = 0; w[15] = 256u;
+    sha_iv(out);
+    chain_compress(out, w);
+}
+__device__ __forceinline__ void chain_node(const uint32_t l[8], const uint32_t r[8], uint32_t out[8]) {
+    uint32_t w[16];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { w[k] = l[k]; w[8 + k] = r[k]; }
+    sha_iv(out);
+    chain_compress(out, w);
+    chain_compress_pad512(out);
+}
+__device__ __forceinline__ uint8_t* chain_layer_ptr(uint8_t* digests, size_t n_leaves, int layer, size_t idx) {
+    return digests + 32 * ((2 * n_leaves - ((2 * n_leaves) >> layer)) + idx);
+}
+__device__ __forceinline__ fe chain_root_pow(const fe* __restrict__ lo, const fe* __restrict__ hi, size_t e) {
+    fe w = fe_load_nc(lo + (e & (((size_t)1 << LO_BITS) - 1)));
+    if (e >> LO_BITS) w = fe_mul(w, fe_load_nc(hi + (e >> LO_BITS)));
+    return w;
+}
+
+// ------------------------------------------------------------------ transcript step kernels
+// absorb `absorb_len` bytes at `absorb` (a Merkle root in HBM), copy them to `copy_out`, then r = next_challenge():
+// r_out[0] = r, r_out[1] = r / 2
+__global__ void chain_challenge_kernel(DevTranscript* tr, const uint8_t* absorb, int absorb_len, uint8_t* copy_out, fe* r_out,
+                                       int want_challenge) {
+    if (threadIdx.x != 0) return;
+    DevTranscript t = *tr;
+    if (absorb_len > 0) {
+        dt_absorb(&t, absorb, absorb_len);
+        if (copy_out)
+            for (int i = 0; i < absorb_len; i++) copy_out[i] = absorb[i];
+        *tr = t;
+    }
+    if (want_challenge) {
+        fe r = dt_challenge(&t);
+        fe_store(r_out, r);
+        fe_store(r_out + 1, fe_half(r));
+    }
+}
+// sumcheck round bookkeeping (src/constraint_system/sumcheck.rs:185-199) from the per-CTA partial sums:
+//   e1, e2 -> e0 = prev - e1 -> (c1, c2) -> absorb -> r -> prev = p(r)
+__global__ void __launch_bounds__(256) chain_sumcheck_finish_kernel(const fe* __restrict__ partials, int nb, fe* prev, DevTranscript* tr,
+                                                                    const uint8_t* absorb, int absorb_len, uint8_t* copy_out,
+                                                                    fe* sc_out, fe* r_out) {
+    __shared__ fe scratch[32];
+    fe a1 = fe_zero(), a2 = fe_zero();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        a1 = fe_add(a1, partials[2 * b]);
+        a2 = fe_add(a2, partials[2 * b + 1]);
+    }
+    fe e1 = block_sum(a1, scratch);
+    fe e2 = block_sum(a2, scratch);
+    if (threadIdx.x != 0) return;
+    DevTranscript t = *tr;
+    if (absorb_len > 0) {
+        dt_absorb(&t, absorb, absorb_len);
+        if (copy_out)
+            for (int i = 0; i < absorb_len; i++) copy_out[i] = absorb[i];
+    }
+    fe e0 = fe_sub(fe_load(prev), e1);
+    fe c2 = fe_half(fe_add(fe_sub(e0, fe_add(e1, e1)), e2));  // (e0 - 2 e1 + e2) / 2
+    fe c1 = fe_sub(fe_sub(e1, e0), c2);
+    dt_absorb_fe(&t, c1);  // nonzero_coeffs = coeffs[1..] (sumcheck.rs:193-197, :263-267)
+    dt_absorb_fe(&t, c2);
+    fe r = dt_challenge(&t);
+    fe_store(prev, fe_add(e0, fe_mul(r, fe_add(c1, fe_mul(r, c2)))));
+    fe_store(sc_out, c1);
+    fe_store(sc_out + 1, c2);
+    fe_store(r_out, r);
+    fe_store(r_out + 1, fe_half(r));
+    *tr = t;
+}
+
+// ------------------------------------------------------------------ fused tail
+__global__ void __launch_bounds__(1024, 1) chain_tail_kernel(TailArgs a) {
+    __shared__ DevTranscript tr;
+    __shared__ fe sh_r[2];
+    __shared__ fe sh_prev;
+    __shared__ fe scratch[32];
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    if (tid == 0) {
+        tr = *a.tr;
+        if (a.m) sh_prev = fe_load(a.prev);
+    }
+    __syncthreads();
+    size_t n = a.n0, h = a.height;
+    int k = a.k0;
+    const size_t n_domain = (size_t)1 << a.log_n0;
+    const uint8_t* pending = a.absorb_first_root ? chain_layer_ptr(a.digests[0], n >> 1, (int)(63 - __clzll((unsigned long long)(n >> 1))), 0) : nullptr;
+    uint8_t* pending_copy = a.absorb_first_root ? a.first_root_out : nullptr;
+    const fe* cur = a.codes[0];
+    for (int round = 0; n > 2; round++, k++) {
+        const size_t half_n = n >> 1;
+        // ---- A: (sumcheck sums ->) challenge
+        if (a.m) {
+            const size_t off = h >> 1;
+            fe_acc s1, s2;
+            acc_zero(s1);
+            acc_zero(s2);
+            for (size_t i = tid; i < off; i += nthreads) {
+                fe m0 = fe_load(a.m + i), m1 = fe_load(a.m + i + off), d0 = fe_load(a.d + i), d1 = fe_load(a.d + i + off);
+                acc_mul_add(s1, m1, d1);
+                acc_mul_add(s2, fe_sub(fe_add(m1, m1), m0), fe_sub(fe_add(d1, d1), d0));
+            }
+            fe e1 = block_sum(acc_reduce(s1), scratch);
+            fe e2 = block_sum(acc_reduce(s2), scratch);
+            if (tid == 0) {
+                if (pending) {
+                    dt_absorb(&tr, pending, 32);
+                    if (pending_copy) for (int i = 0; i < 32; i++) pending_copy[i] = pending[i];
+                }
+                fe e0 = fe_sub(sh_prev, e1);
+                fe c2 = fe_half(fe_add(fe_sub(e0, fe_add(e1, e1)), e2));
+                fe c1 = fe_sub(fe_sub(e1, e0), c2);
+                dt_absorb_fe(&tr, c1);
+                dt_absorb_fe(&tr, c2);
+                fe r = dt_challenge(&tr);
+                sh_prev = fe_add(e0, fe_mul(r, fe_add(c1, fe_mul(r, c2))));
+                fe_store(a.sc_out + 2 * round, c1);
+                fe_store(a.sc_out + 2 * round + 1, c2);
+                sh_r[0] = r;
+                sh_r[1] = fe_half(r);
+            }
+        } else if (tid == 0) {
+            if (pending) {
+                dt_absorb(&tr, pending, 32);
+                if (pending_copy) for (int i = 0; i < 32; i++) pending_copy[i] = pending[i];
+            }
+            fe r = dt_challenge(&tr);
+            sh_r[0] = r;
+            sh_r[1] = fe_half(r);
+        }
+        __syncthreads();
+        const fe r = sh_r[0], rh = sh_r[1];
+        // ---- B: fold the sumcheck tables (sumcheck.rs:234-247)
+        if (a.m) {
+            const size_t off = h >> 1;
+            for (size_t i = tid; i < off; i += nthreads) {
+                fe m0 = fe_load(a.m + i), m1 = fe_load(a.m + i + off), d0 = fe_load(a.d + i), d1 = fe_load(a.d + i + off);
+                fe_store(a.m + i, fe_add(m0, fe_mul(r, fe_sub(m1, m0))));
+                fe_store(a.d + i, fe_add(d0, fe_mul(r, fe_sub(d1, d0))));
+            }
+            h = off;
+        }
+        // ---- C: FRI fold (fri/mod.rs:90-114)
+        fe* next = half_n == 2 ? a.last_out : a.codes[round + 1];
+        for (size_t i = tid; i < half_n; i += nthreads) {
+            fe x = fe_load(cur + i), y = fe_load(cur + i + half_n);
+            fe even = fe_half(fe_add(x, y));
+            fe dd = fe_sub(x, y);
+            if (i != 0) dd = fe_mul(dd, chain_root_pow(a.lo, a.hi, n_domain - (i << k)));
+            fe_store(next + i, fe_add(even, fe_mul(rh, dd)));
+        }
+        __syncthreads();
+        if (half_n == 2) {  // fri/mod.rs:116-126
+            if (tid == 0) {
+                fe x0 = fe_load(next), x1 = fe_load(next + 1);
+                if (!fe_eq(x0, x1)) *a.status = ML_ERR_NOT_RS_CODE;
+                else dt_absorb_fe(&tr, x0);
+            }
+            pending = nullptr;
+            break;
+        }
+        // ---- D: Merkle commit of the folded code (fri/mod.rs:128-133)
+        const size_t L = half_n >> 1;
+        uint8_t* dig = a.digests[round + 1];
+        for (size_t i = tid; i < L; i += nthreads) {
+            uint32_t o[8];
+            chain_leaf(*reinterpret_cast<const uint4*>(next + i), *reinterpret_cast<const uint4*>(next + i + L), o);
+            sha_store_digest(chain_layer_ptr(dig, L, 0, i), o);
+        }
+        __syncthreads();
+        int layer = 0;
+        for (size_t cnt = L; cnt > 1; cnt >>= 1, layer++) {
+            for (size_t i = tid; i < (cnt >> 1); i += nthreads) {
+                uint32_t l[8], rr[8], o[8];
+                sha_load_digest(chain_layer_ptr(dig, L, layer, 2 * i), l);
+                sha_load_digest(chain_layer_ptr(dig, L, layer, 2 * i + 1), rr);
+                chain_node(l, rr, o);
+                sha_store_digest(chain_layer_ptr(dig, L, layer + 1, i), o);
+            }
+            __syncthreads();
+        }
+        pending = chain_layer_ptr(dig, L, layer, 0);
+        pending_copy = a.roots_out + 32 * round;
+        cur = next;
+        n = half_n;
+    }
+    if (tid == 0) {
+        if (pending) {  // only when the loop never ran (n0 <= 2)
+            dt_absorb(&tr, pending, 32);
+            if (pending_copy) for (int i = 0; i < 32; i++) pending_copy[i] = pending[i];
+        }
+        *a.tr = tr;
+        if (a.m) fe_store(a.prev, sh_prev);
+    }
+}
+
+// last fold produced two elements: they must be equal (fri/mod.rs:116-126); absorb the last element
+__global__ void chain_last_kernel(const fe* two, DevTranscript* tr, fe* last_out, int* status) {
+    if (threadIdx.x != 0) return;
+    fe x0 = fe_load(two), x1 = fe_load(two + 1);
+    if (!fe_eq(x0, x1)) { *status = ML_ERR_NOT_RS_CODE; return; }
+    DevTranscript t = *tr;
+    dt_absorb_fe(&t, x0);
+    *tr = t;
+    fe_store(last_out, x0);
+}
+int chain_last_launch(const fe* two, DevTranscript* tr, fe* last_out, int* status, cudaStream_t s) {
+    chain_last_kernel<<<1, 32, 0, s>>>(two, tr, last_out, status);
+    MLB_KERNEL_CHECK();
+    return ML_OK;
+}
+
+int chain_challenge_launch(DevTranscript* tr, const uint8_t* absorb, int absorb_len, uint8_t* copy_out, fe* r_out, bool want_challenge,
+                           cudaStream_t s) {
+    ProfScope prof(PROF_TRANSCRIPT, 0.0, s);
+    chain_challenge_kernel<<<1, 32, 0, s>>>(tr, absorb, absorb_len, copy_out, r_out, want_challenge ? 1 : 0);
+    MLB_KERNEL_CHECK();
+    return ML_OK;
+}
+int chain_sumcheck_finish_launch(const fe* partials, int nb, fe* prev, DevTranscript* tr, const uint8_t* absorb, int absorb_len,
+                                 uint8_t* copy_out, fe* sc_out, fe* r_out, cudaStream_t s) {
+    ProfScope prof(PROF_TRANSCRIPT, 0.0, s);
+    chain_sumcheck_finish_kernel<<<1, 256, 0, s>>>(partials, nb, prev, tr, absorb, absorb_len, copy_out, sc_out, r_out);
+    MLB_KERNEL_CHECK();
+    return ML_OK;
+}
+int chain_tail_launch(const TailArgs& a, cudaStream_t s) {
+    ProfScope prof(PROF_TAIL, 0.0, s);
+    chain_tail_kernel<<<1, 1024, 0, s>>>(a);
+    MLB_KERNEL_CHECK();
+    return ML_OK;
+}
+
+}  // namespace mlb

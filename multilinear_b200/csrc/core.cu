@@ -6,7 +6,7 @@
 namespace mlb {
 
 static thread_local char g_err[512] = "";
-unsigned long long g_kernel_launches = 0;
+std::atomic<unsigned long long> g_kernel_launches{0};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -20,22 +20,29 @@ bool g_prof_on = false;
 struct ProfRec { int id; double bytes; cudaEvent_t e0, e1; bool closed; };
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_event_pool;
+static std::mutex g_prof_mu;
 static cudaEvent_t prof_event() {
     if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
     cudaEvent_t e;
     cudaEventCreate(&e);
     return e;
 }
-void prof_record(int id, double alg_bytes, cudaStream_t s, bool end) {
-    if (!end) {
-        ProfRec r{id, alg_bytes, prof_event(), prof_event(), false};
-        cudaEventRecord(r.e0, s);
-        g_prof.push_back(r);
-    } else {
-        for (size_t i = g_prof.size(); i-- > 0;)
-            if (g_prof[i].id == id && !g_prof[i].closed) { cudaEventRecord(g_prof[i].e1, s); g_prof[i].closed = true; break; }
-    }
+long prof_begin(int id, double alg_bytes, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    ProfRec r{id, alg_bytes, prof_event(), prof_event(), false};
+    cudaEventRecord(r.e0, s);
+    g_prof.push_back(r);
+    return (long)g_prof.size() - 1;
 }
+void prof_end(long rec, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    if (rec < 0 || (size_t)rec >= g_prof.size()) return;
+    cudaEventRecord(g_prof[rec].e1, s);
+    g_prof[rec].closed = true;
+}
+static thread_local cudaStream_t tl_stream = nullptr;
+static thread_local bool tl_stream_set = false;
+cudaStream_t lib_stream(Ctx* ctx) { return tl_stream_set ? tl_stream : ctx->stream; }
 
 static std::mutex g_ctx_mu;
 static std::map<int, Ctx*> g_ctx;
@@ -114,12 +121,14 @@ uint64_t ml_kernel_launches(void) { return g_kernel_launches; }
 
 int ml_profile_enable(int on) { g_prof_on = on != 0; return ML_OK; }
 int ml_profile_reset(void) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     for (auto& r : g_prof) { g_event_pool.push_back(r.e0); g_event_pool.push_back(r.e1); }
     g_prof.clear();
     return ML_OK;
 }
 int ml_profile_get(int id, double* total_ms, uint64_t* launches, double* alg_bytes) {
     MLB_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     double ms = 0, bytes = 0;
     uint64_t n = 0;
     for (auto& r : g_prof) {
@@ -128,6 +137,20 @@ int ml_profile_get(int id, double* total_ms, uint64_t* launches, double* alg_byt
         if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { ms += t; bytes += r.bytes; n++; }
     }
     *total_ms = ms; *launches = n; *alg_bytes = bytes;
+    return ML_OK;
+}
+
+int ml_stream_create(void** out) {
+    cudaStream_t s;
+    MLB_CUDA(cudaStreamCreate(&s));  // blocking stream: ordered against the legacy default stream (event timing in bench.py)
+    *out = (void*)s;
+    return ML_OK;
+}
+int ml_stream_destroy(void* stream) { MLB_CUDA(cudaStreamDestroy((cudaStream_t)stream)); return ML_OK; }
+int ml_stream_synchronize(void* stream) { MLB_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return ML_OK; }
+int ml_set_thread_stream(void* stream, int enable) {
+    tl_stream = (cudaStream_t)stream;
+    tl_stream_set = enable != 0;
     return ML_OK;
 }
 
@@ -153,7 +176,7 @@ static int download(void* host, const void* dev, size_t bytes, cudaStream_t s) {
 // ------------------------------------------------------------------ field vectors
 static int vec2(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
     API_BEGIN
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     Scratch da(s), db(s), dout(s);
     MLB_TRY(upload(da, a, n * 16, s));
     if (b) MLB_TRY(upload(db, b, n * 16, s));
@@ -167,7 +190,7 @@ int ml_fe_mul_vec(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) { 
 int ml_fe_inv_vec(const uint8_t* a, size_t n, uint8_t* out) { return vec2(3, a, nullptr, n, out); }
 int ml_fe_pow_vec(const uint8_t* a, const uint8_t exp_le[16], size_t n, uint8_t* out) {
     API_BEGIN
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     Scratch da(s), dout(s);
     MLB_TRY(upload(da, a, n * 16, s));
     MLB_TRY(dout.alloc(n * 16));
@@ -176,7 +199,7 @@ int ml_fe_pow_vec(const uint8_t* a, const uint8_t exp_le[16], size_t n, uint8_t*
 }
 int ml_fe_from_i64_vec(const int64_t* v, size_t n, uint8_t* out) {
     API_BEGIN
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     Scratch dv(s), dout(s);
     MLB_TRY(upload(dv, v, n * 8, s));
     MLB_TRY(dout.alloc(n * 16));
@@ -204,7 +227,7 @@ int ml_pow2_generator_powers_dev(uint64_t log_size, void* out_dev, void* stream)
 int ml_pow2_generator_powers(uint64_t log_size, uint8_t* out) {
     API_BEGIN
     if (log_size > 40) { set_error("pow_2_generator_powers(%llu): None", (unsigned long long)log_size); return ML_ERR_OUT_OF_RANGE; }
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     Scratch d(s);
     const size_t bytes = ((size_t)16) << log_size;
     MLB_TRY(d.alloc(bytes));
@@ -215,7 +238,7 @@ int ml_bit_reverse_permutation(uint8_t* values, size_t n, size_t elem_bytes) {
     API_BEGIN
     if (n == 0) return ML_OK;
     if (elem_bytes != 16) { set_error("bit_reverse_permutation: only 16-byte (Field128) elements are supported"); return ML_ERR_ARG; }
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     Scratch din(s), dout(s);
     MLB_TRY(upload(din, values, n * 16, s));
     MLB_TRY(dout.alloc(n * 16));
@@ -277,7 +300,7 @@ int ml_reed_solomon_dev(const void* c, size_t n, const uint8_t gen[16], void* co
 }
 static int ntt_host(const uint8_t* in, size_t n, const uint8_t gen[16], uint8_t* out, bool is_intt, bool rs) {
     API_BEGIN
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     const size_t N = rs ? n << ML_LOG_BLOWUP : n;
     if (!is_pow2(N)) { set_error("The number of coeffs must be a power of 2"); return ML_ERR_NOT_POW2; }
     Scratch din(s), dout(s);
@@ -291,7 +314,7 @@ int ml_intt(const uint8_t* e, size_t n, const uint8_t gen[16], uint8_t* c) { ret
 int ml_reed_solomon(const uint8_t* c, size_t n, const uint8_t gen[16], uint8_t* code) { return ntt_host(c, n, gen, code, false, true); }
 int ml_poly_evaluate(const uint8_t* coeffs, size_t n, const uint8_t x[16], uint8_t out[16]) {
     API_BEGIN
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     Scratch d(s);
     MLB_TRY(upload(d, coeffs, n * 16, s));
     hfe r;
@@ -313,7 +336,7 @@ int ml_mle_to_evaluation_dev(const void* c, size_t len, void* e, void* stream) {
 }
 static int mobius_host(const uint8_t* in, size_t len, uint8_t* out, bool sub) {
     API_BEGIN
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     Scratch d(s);
     MLB_TRY(upload(d, in, len * 16, s));
     MLB_TRY(mobius_launch(d.as<fe>(), d.as<fe>(), len, sub, s));
@@ -337,14 +360,14 @@ int ml_mle_evals_evaluate_dev(const void* evals, size_t len, const uint8_t* args
 }
 int ml_mle_evals_evaluate(const uint8_t* evals, size_t len, const uint8_t* args, size_t n_args, uint8_t out[16]) {
     API_BEGIN
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     Scratch d(s);
     MLB_TRY(upload(d, evals, len * 16, s));
     return ml_mle_evals_evaluate_dev(d.p, len, args, n_args, out, s);
 }
 int ml_mle_coeffs_evaluate(const uint8_t* coeffs, size_t len, const uint8_t* args, size_t n_args, uint8_t out[16]) {
     API_BEGIN
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     Scratch d(s);
     MLB_TRY(upload(d, coeffs, len * 16, s));
     std::vector<hfe> a;

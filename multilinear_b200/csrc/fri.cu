@@ -18,8 +18,10 @@ __device__ __forceinline__ fe root_pow(const fe* __restrict__ lo, const fe* __re
 }
 
 // next[i] = half(a + b) + (r/2) * ((a - b) * w^-(i << k))
-__global__ void __launch_bounds__(256) fri_fold_kernel(const fe* __restrict__ cur, size_t half_n, fe* __restrict__ next, fe r_half, int k,
-                                                       int log_n0, const fe* __restrict__ lo, const fe* __restrict__ hi) {
+__global__ void __launch_bounds__(256) fri_fold_kernel(const fe* __restrict__ cur, size_t half_n, fe* __restrict__ next, fe r_half,
+                                                       const fe* __restrict__ r_dev, int k, int log_n0, const fe* __restrict__ lo,
+                                                       const fe* __restrict__ hi) {
+    if (r_dev) r_half = fe_load(r_dev + 1);  // {r, r/2} left in HBM by the transcript kernel
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t n0 = (size_t)1 << log_n0;
@@ -44,20 +46,21 @@ static inline unsigned grid_for(size_t n, size_t cap = 148 * 16) {
     return (unsigned)b;
 }
 
-int fri_fold_launch(Ctx* ctx, const fe* cur, size_t n_cur, fe* next, hfe r, size_t k, int log_n0, cudaStream_t s) {
+int fri_fold_launch(Ctx* ctx, const fe* cur, size_t n_cur, fe* next, hfe r, const fe* r_dev, size_t k, int log_n0, cudaStream_t s) {
     const RootTables* rt;
     MLB_TRY(get_root_tables(ctx, log_n0, s, &rt));
     const size_t half_n = n_cur / 2;
     ProfScope prof(PROF_FRI_FOLD, 24.0 * (double)n_cur, s);  // read n elements, write n/2
-    fri_fold_kernel<<<grid_for(half_n), 256, 0, s>>>(cur, half_n, next, to_dev_fe(hfe_half(r)), (int)k, log_n0, rt->lo, rt->hi);
+    fri_fold_kernel<<<grid_for(half_n), 256, 0, s>>>(cur, half_n, next, to_dev_fe(hfe_half(r)), r_dev, (int)k, log_n0, rt->lo, rt->hi);
     MLB_KERNEL_CHECK();
     return ML_OK;
 }
 
 // batched first fold (batched_fri.rs:124-150): a, b are Horner fingerprints over the batch, acc = acc*rho + c_j
 __global__ void __launch_bounds__(256) fri_batched_fold_kernel(const fe* const* __restrict__ codes, int n_codes, size_t half_n,
-                                                               fe* __restrict__ next, fe rho, fe r_half, int log_n0,
-                                                               const fe* __restrict__ lo, const fe* __restrict__ hi) {
+                                                               fe* __restrict__ next, fe rho, fe r_half, const fe* __restrict__ r_dev,
+                                                               int log_n0, const fe* __restrict__ lo, const fe* __restrict__ hi) {
+    if (r_dev) r_half = fe_load(r_dev + 1);
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t n0 = (size_t)1 << log_n0;
@@ -74,14 +77,14 @@ __global__ void __launch_bounds__(256) fri_batched_fold_kernel(const fe* const* 
         fe_store(next + i, fe_add(even, fe_mul(r_half, d)));
     }
 }
-int fri_batched_fold_launch(Ctx* ctx, const fe* const* codes, size_t n_codes, size_t n, fe* next, hfe fingerprint_r, hfe r, int log_n0,
-                            cudaStream_t s) {
+int fri_batched_fold_launch(Ctx* ctx, const fe* const* codes, size_t n_codes, size_t n, fe* next, hfe fingerprint_r, hfe r,
+                            const fe* r_dev, int log_n0, cudaStream_t s) {
     const RootTables* rt;
     MLB_TRY(get_root_tables(ctx, log_n0, s, &rt));
     const size_t half_n = n / 2;
     ProfScope prof(PROF_FRI_FOLD, 16.0 * (double)n * (double)n_codes + 8.0 * (double)n, s);
     fri_batched_fold_kernel<<<grid_for(half_n), 256, 0, s>>>(codes, (int)n_codes, half_n, next, to_dev_fe(fingerprint_r),
-                                                              to_dev_fe(hfe_half(r)), log_n0, rt->lo, rt->hi);
+                                                              to_dev_fe(hfe_half(r)), r_dev, log_n0, rt->lo, rt->hi);
     MLB_KERNEL_CHECK();
     return ML_OK;
 }

@@ -1,5 +1,6 @@
 // Internal declarations shared by the .cu translation units of libmultilinear_b200.so.
 #pragma once
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -16,7 +17,7 @@ namespace mlb {
 
 // ------------------------------------------------------------------ errors / launch accounting
 void set_error(const char* fmt, ...);
-extern unsigned long long g_kernel_launches;
+extern std::atomic<unsigned long long> g_kernel_launches;
 #define MLB_COUNT_LAUNCH() (++::mlb::g_kernel_launches)
 
 #define MLB_CUDA(expr)                                                                          \
@@ -44,13 +45,14 @@ extern unsigned long long g_kernel_launches;
 
 // ------------------------------------------------------------------ optional per-kernel timing (CUDA events on the launch stream)
 enum ProfId { PROF_NTT_PASS = 0, PROF_MERKLE_LEAF, PROF_MERKLE_NODES, PROF_MERKLE_TOP, PROF_FRI_FOLD, PROF_SUMCHECK_SUMS,
-              PROF_SUMCHECK_FOLD, PROF_MOBIUS, PROF_EQ_TABLE, PROF_BITREV, PROF_GATHER, PROF_COUNT };
+              PROF_SUMCHECK_FOLD, PROF_MOBIUS, PROF_EQ_TABLE, PROF_BITREV, PROF_GATHER, PROF_TAIL, PROF_TRANSCRIPT, PROF_COUNT };
 extern bool g_prof_on;
-void prof_record(int id, double alg_bytes, cudaStream_t s, bool end);
-struct ProfScope {  // brackets the kernel launches issued inside its lifetime
-    int id; cudaStream_t s; bool on;
-    ProfScope(int id_, double alg_bytes, cudaStream_t s_) : id(id_), s(s_), on(g_prof_on) { if (on) prof_record(id, alg_bytes, s, false); }
-    ~ProfScope() { if (on) prof_record(id, 0, s, true); }
+long prof_begin(int id, double alg_bytes, cudaStream_t s);  // returns a record index
+void prof_end(long rec, cudaStream_t s);
+struct ProfScope {  // brackets the kernel launches issued inside its lifetime (thread-safe: several host threads may drive streams)
+    cudaStream_t s; long rec;
+    ProfScope(int id, double alg_bytes, cudaStream_t s_) : s(s_), rec(g_prof_on ? prof_begin(id, alg_bytes, s_) : -1) {}
+    ~ProfScope() { if (rec >= 0) prof_end(rec, s); }
 };
 
 // ------------------------------------------------------------------ host scalar field (transcript challenges,
@@ -125,6 +127,8 @@ struct Ctx {
     int sm_count = 148;
 };
 int get_ctx(Ctx** out);  // context of the current device (lazily created)
+// stream used by host-pointer entry points: the calling thread's override (ml_set_thread_stream) or the context stream
+cudaStream_t lib_stream(Ctx* ctx);
 int get_root_tables(Ctx* ctx, int log_n, cudaStream_t s, const RootTables** out);
 
 // stream-ordered scratch allocation
@@ -154,13 +158,45 @@ int merkle_bytes_launch(const uint8_t* const* data_dev_ptrs, size_t n_batches, s
 int merkle_batched_rs_launch(const fe* const* codes_dev_ptrs, size_t n_codes, size_t n_code, uint8_t* digests, cudaStream_t s);
 int merkle_batched_pairs_launch(const uint8_t* const* pairs_dev_ptrs, size_t n_codes, size_t n_leaves, uint8_t* digests, cudaStream_t s);
 int merkle_upper_launch(uint8_t* digests, size_t n_leaves, cudaStream_t s);  // layers 1.. from layer 0
-// fri.cu
-int fri_fold_launch(Ctx* ctx, const fe* cur, size_t n_cur, fe* next, hfe r, size_t k, int log_n0, cudaStream_t s);
-int fri_batched_fold_launch(Ctx* ctx, const fe* const* codes_dev_ptrs, size_t n_codes, size_t n, fe* next, hfe fingerprint_r, hfe r, int log_n0, cudaStream_t s);
+// fri.cu — r_dev (optional): device pointer to {r, r/2} written by a transcript kernel; overrides the host value r
+int fri_fold_launch(Ctx* ctx, const fe* cur, size_t n_cur, fe* next, hfe r, const fe* r_dev, size_t k, int log_n0, cudaStream_t s);
+int fri_batched_fold_launch(Ctx* ctx, const fe* const* codes_dev_ptrs, size_t n_codes, size_t n, fe* next, hfe fingerprint_r, hfe r,
+                            const fe* r_dev, int log_n0, cudaStream_t s);
 int fingerprint_rows_launch(const fe* const* polys_dev_ptrs, size_t n_polys, size_t n, hfe r, fe* out, cudaStream_t s);
 // sumcheck.cu
 int sumcheck_sums_launch(Ctx* ctx, const fe* m, const fe* d, size_t height, hfe* s1, hfe* s2, cudaStream_t s);
 int sumcheck_partial_sum_launch(Ctx* ctx, const fe* m, const fe* d, size_t height, hfe r, hfe* out, cudaStream_t s);
-int sumcheck_fold_launch(fe* m, fe* d, size_t height, hfe r, cudaStream_t s);
+int sumcheck_fold_launch(fe* m, fe* d, size_t height, hfe r, const fe* r_dev, cudaStream_t s);
+int sumcheck_sums_partials_launch(const fe* m, const fe* d, size_t height, fe* partials /* 2 per CTA */, int* n_blocks, cudaStream_t s);
+int sumcheck_max_blocks();
+// chain.cu — device-resident transcript steps and the fused tail of the fold chain
+struct DevTranscript;
+static const int TAIL_LOG = 12;          // the tail kernel takes over once the current code has <= 2^TAIL_LOG elements
+static const int TAIL_MAX_ROUNDS = 12;
+struct TailArgs {
+    fe* codes[TAIL_MAX_ROUNDS + 1];         // codes[0]: current committed layer (n0 elements); codes[i+1]: output of tail round i
+    uint8_t* digests[TAIL_MAX_ROUNDS + 1];  // digests[i]: all Merkle layers of codes[i]
+    size_t n0;
+    int k0, log_n0;
+    const fe* lo;
+    const fe* hi;
+    DevTranscript* tr;
+    uint8_t* roots_out;       // 32 bytes per committed tail layer
+    uint8_t* first_root_out;  // where to copy codes[0]'s root when it is absorbed here
+    fe* last_out;             // 2 elements; [0] = last_element
+    int* status;
+    int absorb_first_root;
+    fe* m;                    // sumcheck tables (nullptr: plain FRI)
+    fe* d;
+    size_t height;
+    fe* prev;
+    fe* sc_out;               // (c1, c2) per tail round
+};
+int chain_challenge_launch(DevTranscript* tr, const uint8_t* absorb, int absorb_len, uint8_t* copy_out, fe* r_out, bool want_challenge,
+                           cudaStream_t s);
+int chain_sumcheck_finish_launch(const fe* partials, int nb, fe* prev, DevTranscript* tr, const uint8_t* absorb, int absorb_len,
+                                 uint8_t* copy_out, fe* sc_out, fe* r_out, cudaStream_t s);
+int chain_tail_launch(const TailArgs& a, cudaStream_t s);
+int chain_last_launch(const fe* two, DevTranscript* tr, fe* last_out, int* status, cudaStream_t s);
 
 }  // namespace mlb

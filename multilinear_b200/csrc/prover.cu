@@ -4,6 +4,7 @@
 #include "field.cuh"
 #include "handles.h"
 #include "internal.h"
+#include "transcript.cuh"
 
 using namespace mlb;
 
@@ -37,6 +38,9 @@ int d2h_sync(void* dst, const void* src, size_t bytes, cudaStream_t s) {
     MLB_CUDA(cudaStreamSynchronize(s));
     return ML_OK;
 }
+int fri_push_layer(ml_fri* f, fe* code, size_t n, bool owns_code, cudaStream_t s, bool build_tree);
+int fold_chain_dev(Ctx* ctx, ml_fri* f, struct BatchedFri* b, ml_sumcheck* sc, hfe prev, hfe* sc_out, size_t k_start, bool pending,
+                   ml_transcript* t, cudaStream_t s);
 void absorb_fe(ml_transcript* t, hfe x) {
     uint8_t b[16];
     hfe_store(b, x);
@@ -169,7 +173,7 @@ int fri_fold_step_impl(Ctx* ctx, ml_fri* f, size_t k, hfe r, ml_transcript* t, c
     if ((half_n << k) > ((size_t)1 << f->log_n0)) { set_error("fold_step: k = %zu out of range for this domain", k); return ML_ERR_ARG; }
     fe* next;
     MLB_TRY(pmalloc((void**)&next, half_n * 16, s));
-    int st = fri_fold_launch(ctx, last.code, n, next, r, k, f->log_n0, s);
+    int st = fri_fold_launch(ctx, last.code, n, next, r, nullptr, k, f->log_n0, s);
     if (st != ML_OK) { pfree(next, s); return st; }
     return fold_finish(f, next, half_n, t, s);
 }
@@ -178,6 +182,15 @@ int fri_init_owned(ml_fri** out, fe* code, size_t n, bool owns, ml_transcript* t
     f->log_n0 = (int)ilog2(n);
     f->stream = s;
     int st = fri_commit_layer(f, code, n, owns, t, s);
+    if (st != ML_OK) { if (owns) pfree(code, s); free_fri(f); return st; }
+    *out = f;
+    return ML_OK;
+}
+int fri_new_unabsorbed(ml_fri** out, fe* code, size_t n, bool owns, cudaStream_t s) {
+    ml_fri* f = new ml_fri();
+    f->log_n0 = (int)ilog2(n);
+    f->stream = s;
+    int st = fri_push_layer(f, code, n, owns, s, true);
     if (st != ML_OK) { if (owns) pfree(code, s); free_fri(f); return st; }
     *out = f;
     return ML_OK;
@@ -317,7 +330,7 @@ int sumcheck_round(Ctx* ctx, ml_sumcheck* sc, size_t total_degree, hfe* previous
     for (size_t i = 1; i <= total_degree; i++) { nonzero_out[i - 1] = coeffs[i]; absorb_fe(t, coeffs[i]); }  // :193-197
     hfe r = challenge(t);                                                 // :198
     *previous_sum = poly_eval(coeffs, r);                                 // :199
-    MLB_TRY(sumcheck_fold_launch(sc->matrix, sc->delta, sc->height, r, s));  // :200
+    MLB_TRY(sumcheck_fold_launch(sc->matrix, sc->delta, sc->height, r, nullptr, s));  // :200
     sc->height >>= 1;
     *r_out = r;
     return ML_OK;
@@ -362,6 +375,167 @@ int encode_poly(Ctx* ctx, const fe* evals_dev, size_t n, fe** code_out, cudaStre
     int st = ntt_launch(ctx, rev.as<fe>(), code, log_domain, false, true, s);
     if (st != ML_OK) { pfree(code, s); return st; }
     *code_out = code;
+    return ML_OK;
+}
+
+// ------------------------------------------------------------------ sync-free fold chain (device transcript)
+struct BatchedFri;
+int bfri_first_fold_dev(Ctx* ctx, BatchedFri* b, const fe* r_dev, fe** next_out, size_t* half_n_out, cudaStream_t s);
+
+// build the tree of a layer without reading the root back (the chain absorbs it on the device)
+int fri_push_layer(ml_fri* f, fe* code, size_t n, bool owns_code, cudaStream_t s, bool build_tree) {
+    ml_merkle* m;
+    MLB_TRY(new_merkle(n / 2, s, &m));
+    m->kind = ml_merkle::RS_CODE;
+    m->item_bytes = 32;
+    m->data.push_back(code);
+    m->owns_data = false;
+    if (build_tree) {
+        int st = merkle_rs_launch(code, n, m->digests, s);
+        if (st != ML_OK) { free_merkle(m); return st; }
+    }
+    ml_fri::Layer L;
+    L.code = code; L.n = n; L.owns_code = owns_code; L.tree = m;
+    f->layers.push_back(L);
+    return ML_OK;
+}
+uint8_t* layer_root_ptr(const ml_fri::Layer& L) {
+    const size_t leaves = L.n / 2;
+    return L.tree->digests + 32 * merkle_layer_offset(leaves, (int)ilog2(leaves));
+}
+
+// Runs fold steps k_start.. to the end with the transcript advanced on the device.
+//   f       : FriProverData; its last layer is the current code (tree built).  Empty only with `b` (batched first fold).
+//   pending : the last layer's root has not been absorbed yet
+//   sc/prev : sumcheck tables + running claim for the PCS interleave (nullptr/unused for plain FRI)
+//   sc_out  : host array receiving (c1, c2) per round from k_start on
+// On return every layer root, last_element and the host transcript are up to date.
+int fold_chain_dev(Ctx* ctx, ml_fri* f, BatchedFri* b, ml_sumcheck* sc, hfe prev, hfe* sc_out, size_t k_start, bool pending,
+                   ml_transcript* t, cudaStream_t s) {
+    const size_t total_steps = (size_t)f->log_n0 - ML_LOG_BLOWUP;
+    if (k_start >= total_steps) {
+        if (!f->has_last) { set_error("fold: last_element is None"); return ML_ERR_SIZE; }
+        return ML_OK;
+    }
+    // one scratch block: transcript | r, r/2 | prev | last[2] | status | roots[64] | sc[2*64] | partials
+    const int max_nb = sumcheck_max_blocks();
+    Scratch blk(s);
+    const size_t off_tr = 0, off_r = 128, off_prev = off_r + 32, off_last = off_prev + 16, off_status = off_last + 32,
+                 off_roots = off_status + 16, off_sc = off_roots + 64 * 32, off_part = off_sc + 2 * 64 * 16,
+                 total = off_part + (size_t)(2 * max_nb + 2) * 16;
+    MLB_TRY(blk.alloc(total));
+    uint8_t* base = blk.as<uint8_t>();
+    DevTranscript* tr_dev = (DevTranscript*)(base + off_tr);
+    fe* r_dev = (fe*)(base + off_r);
+    fe* prev_dev = (fe*)(base + off_prev);
+    fe* last_dev = (fe*)(base + off_last);
+    int* status_dev = (int*)(base + off_status);
+    uint8_t* roots_dev = base + off_roots;
+    fe* sc_dev = (fe*)(base + off_sc);
+    fe* partials = (fe*)(base + off_part);
+    MLB_CUDA(cudaMemsetAsync(base, 0, off_part, s));
+    MLB_TRY(h2d(tr_dev, &t->sha, sizeof(DevTranscript), s));
+    if (sc) {
+        uint8_t pb[16];
+        hfe_store(pb, prev);
+        MLB_TRY(h2d(prev_dev, pb, 16, s));
+    }
+    const RootTables* rt;
+    MLB_TRY(get_root_tables(ctx, f->log_n0, s, &rt));
+
+    const size_t first_new_layer = f->layers.size() - (pending ? 1 : 0);  // roots to fetch afterwards: layers >= this index
+    bool used_tail = false;
+    size_t k = k_start;
+    for (; k < total_steps; k++) {
+        const bool batched_round = f->layers.empty();
+        const size_t n = batched_round ? ((size_t)1 << f->log_n0) : f->layers.back().n;
+        if (n <= ((size_t)1 << ML_LOG_BLOWUP)) break;
+        const size_t half_n = n >> 1;
+        if (!batched_round && n <= ((size_t)1 << TAIL_LOG)) {
+            // ---- fused tail: every remaining round in one launch
+            TailArgs a;
+            memset(&a, 0, sizeof a);
+            const size_t tail_base = f->layers.size() - 1;
+            a.codes[0] = f->layers.back().code;
+            a.digests[0] = f->layers.back().tree->digests;
+            a.n0 = n; a.k0 = (int)k; a.log_n0 = f->log_n0;
+            a.lo = rt->lo; a.hi = rt->hi;
+            a.tr = tr_dev;
+            a.roots_out = roots_dev + 32 * (tail_base + 1);
+            a.first_root_out = roots_dev + 32 * tail_base;
+            a.last_out = last_dev;
+            a.status = status_dev;
+            a.absorb_first_root = pending ? 1 : 0;
+            if (sc) { a.m = sc->matrix; a.d = sc->delta; a.height = sc->height; a.prev = prev_dev; a.sc_out = sc_dev + 2 * (k - k_start); }
+            int i = 1;
+            for (size_t m = half_n; m > 2; m >>= 1, i++) {  // committed tail layers: sizes half_n .. 4
+                fe* code;
+                MLB_TRY(pmalloc((void**)&code, m * 16, s));
+                int st = fri_push_layer(f, code, m, true, s, false);
+                if (st != ML_OK) { pfree(code, s); return st; }
+                a.codes[i] = code;
+                a.digests[i] = f->layers.back().tree->digests;
+            }
+            MLB_TRY(chain_tail_launch(a, s));
+            if (sc) { size_t rounds = ilog2(n) - 1; sc->height >>= rounds; }
+            pending = false;
+            used_tail = true;
+            k = total_steps;
+            break;
+        }
+        // ---- challenge (absorbing the pending root first)
+        const uint8_t* absorb = pending ? layer_root_ptr(f->layers.back()) : nullptr;
+        uint8_t* copy_out = pending ? roots_dev + 32 * (f->layers.size() - 1) : nullptr;
+        if (sc) {
+            int nb = 0;
+            MLB_TRY(sumcheck_sums_partials_launch(sc->matrix, sc->delta, sc->height, partials, &nb, s));
+            MLB_TRY(chain_sumcheck_finish_launch(partials, nb, prev_dev, tr_dev, absorb, pending ? 32 : 0, copy_out, sc_dev + 2 * (k - k_start), r_dev, s));
+            MLB_TRY(sumcheck_fold_launch(sc->matrix, sc->delta, sc->height, 0, r_dev, s));
+            sc->height >>= 1;
+        } else {
+            MLB_TRY(chain_challenge_launch(tr_dev, absorb, pending ? 32 : 0, copy_out, r_dev, true, s));
+        }
+        pending = false;
+        // ---- fold
+        fe* next = nullptr;
+        if (batched_round) {
+            size_t hn = 0;
+            MLB_TRY(bfri_first_fold_dev(ctx, b, r_dev, &next, &hn, s));
+        } else {
+            MLB_TRY(pmalloc((void**)&next, half_n * 16, s));
+            int st = fri_fold_launch(ctx, f->layers.back().code, n, next, 0, r_dev, k, f->log_n0, s);
+            if (st != ML_OK) { pfree(next, s); return st; }
+        }
+        if (half_n == ((size_t)1 << ML_LOG_BLOWUP)) {  // only reachable from a batched first fold of a 4-element domain
+            int st = chain_last_launch(next, tr_dev, last_dev, status_dev, s);
+            pfree(next, s);
+            MLB_TRY(st);
+            used_tail = true;
+            k = total_steps;
+            break;
+        }
+        int st = fri_push_layer(f, next, half_n, true, s, true);
+        if (st != ML_OK) { pfree(next, s); return st; }
+        pending = true;
+    }
+    if (pending) {  // chain ended on a committed layer (cannot happen for well-formed sizes, kept for safety)
+        MLB_TRY(chain_challenge_launch(tr_dev, layer_root_ptr(f->layers.back()), 32, roots_dev + 32 * (f->layers.size() - 1), r_dev, false, s));
+    }
+    // ---- single synchronisation point: roots, last element, status, coefficients, transcript
+    std::vector<uint8_t> host(off_part);
+    MLB_TRY(d2h_sync(host.data(), base, off_part, s));
+    int status = 0;
+    memcpy(&status, host.data() + off_status, sizeof status);
+    if (status != 0) { set_error("not an RS code"); return status; }
+    for (size_t j = first_new_layer; j < f->layers.size(); j++) memcpy(f->layers[j].tree->root, host.data() + off_roots + 32 * j, 32);
+    if (used_tail) {
+        f->last = hfe_load(host.data() + off_last);
+        f->has_last = true;
+    }
+    if (sc && sc_out)
+        for (size_t i = 0; i < 2 * (total_steps - k_start); i++) sc_out[i] = hfe_load(host.data() + off_sc + 16 * i);
+    memcpy(&t->sha, host.data() + off_tr, sizeof(DevTranscript));
+    if (!f->has_last) { set_error("fold: last_element is None"); return ML_ERR_SIZE; }
     return ML_OK;
 }
 
@@ -551,9 +725,19 @@ int bfri_batched_fold_step(Ctx* ctx, BatchedFri* b, hfe r, ml_transcript* t, cud
     const size_t half_n = n >> 1;
     fe* next;
     MLB_TRY(pmalloc((void**)&next, half_n * 16, s));
-    int st = fri_batched_fold_launch(ctx, b->codes_ptrs_dev, b->codes.size(), n, next, b->fingerprint_r, r, b->fri->log_n0, s);
+    int st = fri_batched_fold_launch(ctx, b->codes_ptrs_dev, b->codes.size(), n, next, b->fingerprint_r, r, nullptr, b->fri->log_n0, s);
     if (st != ML_OK) { pfree(next, s); return st; }
     return fold_finish(b->fri, next, half_n, t, s);
+}
+int bfri_first_fold_dev(Ctx* ctx, BatchedFri* b, const fe* r_dev, fe** next_out, size_t* half_n_out, cudaStream_t s) {
+    const size_t half_n = b->n >> 1;
+    fe* next;
+    MLB_TRY(pmalloc((void**)&next, half_n * 16, s));
+    int st = fri_batched_fold_launch(ctx, b->codes_ptrs_dev, b->codes.size(), b->n, next, b->fingerprint_r, 0, r_dev, b->fri->log_n0, s);
+    if (st != ML_OK) { pfree(next, s); return st; }
+    *next_out = next;
+    *half_n_out = half_n;
+    return ML_OK;
 }
 // query phase of BatchedFriProof::prove / BatchedPCSProof::prove (batched_fri.rs:207-225, 296-308)
 int bfri_assemble(BatchedFri* b, ml_transcript* t, ml_bfri_proof* p, cudaStream_t s) {
@@ -657,7 +841,7 @@ int ml_merkle_batch_commit(const uint8_t* const* data, size_t n_batches, size_t 
     API_BEGIN
     if (n_batches == 0) { set_error("Data must not be empty"); return ML_ERR_SIZE; }
     if (!is_pow2(n_items)) { set_error("Data length must be a power of two"); return ML_ERR_NOT_POW2; }
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     ml_merkle* m;
     MLB_TRY(new_merkle(n_items, s, &m));
     m->kind = ml_merkle::BYTES;
@@ -701,12 +885,12 @@ size_t ml_merkle_layer_len(const ml_merkle* m, size_t layer) { return m->n_leave
 int ml_merkle_layer(const ml_merkle* m, size_t layer, uint8_t* out) {
     API_BEGIN
     if (layer > ilog2(m->n_leaves)) return ML_ERR_OUT_OF_RANGE;
-    return d2h_sync(out, m->digests + 32 * merkle_layer_offset(m->n_leaves, layer), (m->n_leaves >> layer) * 32, ctx->stream);
+    return d2h_sync(out, m->digests + 32 * merkle_layer_offset(m->n_leaves, layer), (m->n_leaves >> layer) * 32, lib_stream(ctx));
 }
 int ml_merkle_open(const ml_merkle* m, size_t index, uint8_t* value, uint8_t* digests, uint8_t* dirs, size_t* path_len) {
     API_BEGIN
     if (index >= m->n_leaves) { set_error("open(%zu): None", index); return ML_ERR_OUT_OF_RANGE; }
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     const int depth = (int)ilog2(m->n_leaves);
     const size_t nb = m->n_batches ? m->n_batches : 1;
     const size_t vbytes = nb * m->item_bytes;
@@ -760,7 +944,7 @@ int ml_fri_init_dev(const void* code_dev, size_t n, ml_transcript* t, void* stre
 int ml_fri_init(const uint8_t* code_host, size_t n, ml_transcript* t, ml_fri** out) {
     API_BEGIN
     MLB_TRY(check_code_len(n));
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     fe* code;
     MLB_TRY(pmalloc((void**)&code, n * 16, s));
     MLB_CUDA(cudaMemcpyAsync(code, code_host, n * 16, cudaMemcpyHostToDevice, s));
@@ -777,13 +961,21 @@ static int check_gen_pows(const ml_fri* f, const uint8_t* gen_pows, size_t gen_p
 int ml_fri_fold_step(ml_fri* f, const uint8_t* gen_pows, size_t gen_pows_len, size_t k, const uint8_t r[16], ml_transcript* t) {
     API_BEGIN
     MLB_TRY(check_gen_pows(f, gen_pows, gen_pows_len));
-    return fri_fold_step_impl(ctx, f, k, hfe_load(r), t, ctx->stream);
+    return fri_fold_step_impl(ctx, f, k, hfe_load(r), t, lib_stream(ctx));
+}
+static int fri_from_copy(const void* src, size_t n, bool src_on_device, cudaStream_t s, ml_fri** out) {
+    MLB_TRY(check_code_len(n));
+    fe* code;
+    MLB_TRY(pmalloc((void**)&code, n * 16, s));
+    cudaError_t e = cudaMemcpyAsync(code, src, n * 16, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { pfree(code, s); set_error("copy failed: %s", cudaGetErrorString(e)); return ML_ERR_CUDA; }
+    return fri_new_unabsorbed(out, code, n, true, s);
 }
 int ml_fri_fold_dev(const void* code_dev, size_t n, ml_transcript* t, void* stream, ml_fri** out) {
     API_BEGIN
     ml_fri* f;
-    MLB_TRY(ml_fri_init_dev(code_dev, n, t, stream, &f));
-    int st = fri_fold_all(ctx, f, t, ST(stream));
+    MLB_TRY(fri_from_copy(code_dev, n, true, ST(stream), &f));
+    int st = fold_chain_dev(ctx, f, nullptr, nullptr, 0, nullptr, 0, true, t, ST(stream));
     if (st != ML_OK) { free_fri(f); return st; }
     *out = f;
     return ML_OK;
@@ -791,9 +983,9 @@ int ml_fri_fold_dev(const void* code_dev, size_t n, ml_transcript* t, void* stre
 int ml_fri_fold(const uint8_t* gen_pows, size_t gen_pows_len, const uint8_t* code, size_t n, ml_transcript* t, ml_fri** out) {
     API_BEGIN
     ml_fri* f;
-    MLB_TRY(ml_fri_init(code, n, t, &f));
+    MLB_TRY(fri_from_copy(code, n, false, lib_stream(ctx), &f));
     int st = check_gen_pows(f, gen_pows, gen_pows_len);
-    if (st == ML_OK) st = fri_fold_all(ctx, f, t, ctx->stream);
+    if (st == ML_OK) st = fold_chain_dev(ctx, f, nullptr, nullptr, 0, nullptr, 0, true, t, lib_stream(ctx));
     if (st != ML_OK) { free_fri(f); return st; }
     *out = f;
     return ML_OK;
@@ -816,7 +1008,7 @@ __global__ void pairs_kernel(const fe* __restrict__ code, size_t half, uint4* __
 int ml_fri_tree_data(const ml_fri* f, size_t i, uint8_t* pairs_out) {
     API_BEGIN
     if (i >= f->layers.size()) return ML_ERR_OUT_OF_RANGE;
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     const ml_fri::Layer& L = f->layers[i];
     Scratch d(s);
     MLB_TRY(d.alloc(L.n * 16));
@@ -840,7 +1032,7 @@ int ml_fri_open_query_at(const ml_fri* f, size_t index, uint8_t* values, uint8_t
     if (f->layers.empty() || index >= f->layers[0].n / 2) { set_error("open_query_at: index out of range"); return ML_ERR_OUT_OF_RANGE; }
     std::vector<size_t> idx(1, index);
     std::vector<QueryH> q;
-    MLB_TRY(fri_open_queries(f, idx, q, ctx->stream));
+    MLB_TRY(fri_open_queries(f, idx, q, lib_stream(ctx)));
     size_t doff = 0;
     for (size_t j = 0; j < q[0].paths.size(); j++) {
         const PathH& p = q[0].paths[j];
@@ -853,7 +1045,7 @@ int ml_fri_open_query_at(const ml_fri* f, size_t index, uint8_t* values, uint8_t
     return ML_OK;
 }
 static int fri_prove_from(Ctx* ctx, ml_fri* f, size_t n, ml_transcript* t, cudaStream_t s, ml_fri_proof** out) {
-    int st = fri_fold_all(ctx, f, t, s);
+    int st = fold_chain_dev(ctx, f, nullptr, nullptr, 0, nullptr, 0, true, t, s);
     ml_fri_proof* p = nullptr;
     if (st == ML_OK) {
         p = new ml_fri_proof();
@@ -867,16 +1059,16 @@ static int fri_prove_from(Ctx* ctx, ml_fri* f, size_t n, ml_transcript* t, cudaS
 int ml_fri_prove_dev(const void* code_dev, size_t n, ml_transcript* t, void* stream, ml_fri_proof** out) {
     API_BEGIN
     ml_fri* f;
-    MLB_TRY(ml_fri_init_dev(code_dev, n, t, stream, &f));
+    MLB_TRY(fri_from_copy(code_dev, n, true, ST(stream), &f));
     return fri_prove_from(ctx, f, n, t, ST(stream), out);
 }
 int ml_fri_prove(const uint8_t* code, size_t n, const uint8_t* gen_pows, size_t gen_pows_len, ml_transcript* t, ml_fri_proof** out) {
     API_BEGIN
     ml_fri* f;
-    MLB_TRY(ml_fri_init(code, n, t, &f));
+    MLB_TRY(fri_from_copy(code, n, false, lib_stream(ctx), &f));
     int st = check_gen_pows(f, gen_pows, gen_pows_len);
     if (st != ML_OK) { free_fri(f); return st; }
-    return fri_prove_from(ctx, f, n, t, ctx->stream, out);
+    return fri_prove_from(ctx, f, n, t, lib_stream(ctx), out);
 }
 static int rs_encode_owned(Ctx* ctx, const void* coeffs_dev, size_t n, fe** code_out, cudaStream_t s) {
     const size_t N = n << ML_LOG_BLOWUP;
@@ -894,8 +1086,8 @@ int ml_rs_fri_fold_dev(const void* coeffs_dev, size_t n, ml_transcript* t, void*
     fe* code;
     MLB_TRY(rs_encode_owned(ctx, coeffs_dev, n, &code, s));
     ml_fri* f;
-    MLB_TRY(fri_init_owned(&f, code, n << ML_LOG_BLOWUP, true, t, s));
-    int st = fri_fold_all(ctx, f, t, s);
+    MLB_TRY(fri_new_unabsorbed(&f, code, n << ML_LOG_BLOWUP, true, s));
+    int st = fold_chain_dev(ctx, f, nullptr, nullptr, 0, nullptr, 0, true, t, s);
     if (st != ML_OK) { free_fri(f); return st; }
     *out = f;
     return ML_OK;
@@ -906,12 +1098,12 @@ int ml_rs_fri_prove_dev(const void* coeffs_dev, size_t n, ml_transcript* t, void
     fe* code;
     MLB_TRY(rs_encode_owned(ctx, coeffs_dev, n, &code, s));
     ml_fri* f;
-    MLB_TRY(fri_init_owned(&f, code, n << ML_LOG_BLOWUP, true, t, s));
+    MLB_TRY(fri_new_unabsorbed(&f, code, n << ML_LOG_BLOWUP, true, s));
     return fri_prove_from(ctx, f, n << ML_LOG_BLOWUP, t, s, out);
 }
 int ml_rs_fri_prove(const uint8_t* coeffs, size_t n, ml_transcript* t, ml_fri_proof** out) {
     API_BEGIN
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     Scratch d(s);
     MLB_TRY(d.alloc(n * 16));
     MLB_TRY(h2d(d.p, coeffs, n * 16, s));
@@ -943,7 +1135,7 @@ int ml_fri_proof_serialize(const ml_fri_proof* p, uint8_t* out) { Writer w(out);
 // ================================================================== sumcheck
 int ml_sumcheck_build_tables_for_pcs(const uint8_t* inputs, size_t n_vars, const uint8_t* evals, size_t height, ml_sumcheck** out) {
     API_BEGIN
-    return sumcheck_build(ctx, inputs, n_vars, evals, false, height, ctx->stream, out);
+    return sumcheck_build(ctx, inputs, n_vars, evals, false, height, lib_stream(ctx), out);
 }
 int ml_sumcheck_build_tables_for_pcs_dev(const uint8_t* inputs, size_t n_vars, const void* evals_dev, size_t height, void* stream,
                                          ml_sumcheck** out) {
@@ -954,21 +1146,21 @@ void ml_sumcheck_free(ml_sumcheck* s) { free_sumcheck(s); }
 size_t ml_sumcheck_height(const ml_sumcheck* s) { return s->height; }
 int ml_sumcheck_tables(const ml_sumcheck* sc, uint8_t* matrix_out, uint8_t* delta_out) {
     API_BEGIN
-    MLB_TRY(d2h_sync(matrix_out, sc->matrix, sc->height * 16, ctx->stream));
-    return d2h_sync(delta_out, sc->delta, sc->height * 16, ctx->stream);
+    MLB_TRY(d2h_sync(matrix_out, sc->matrix, sc->height * 16, lib_stream(ctx)));
+    return d2h_sync(delta_out, sc->delta, sc->height * 16, lib_stream(ctx));
 }
 int ml_sumcheck_partial_sum(const ml_sumcheck* sc, const uint8_t r[16], uint8_t out[16]) {
     API_BEGIN
     hfe o;
-    MLB_TRY(sumcheck_partial_sum_launch(ctx, sc->matrix, sc->delta, sc->height, hfe_load(r), &o, ctx->stream));
+    MLB_TRY(sumcheck_partial_sum_launch(ctx, sc->matrix, sc->delta, sc->height, hfe_load(r), &o, lib_stream(ctx)));
     hfe_store(out, o);
     return ML_OK;
 }
 int ml_sumcheck_fold(ml_sumcheck* sc, const uint8_t r[16]) {
     API_BEGIN
-    MLB_TRY(sumcheck_fold_launch(sc->matrix, sc->delta, sc->height, hfe_load(r), ctx->stream));
+    MLB_TRY(sumcheck_fold_launch(sc->matrix, sc->delta, sc->height, hfe_load(r), nullptr, lib_stream(ctx)));
     sc->height >>= 1;
-    MLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MLB_CUDA(cudaStreamSynchronize(lib_stream(ctx)));
     return ML_OK;
 }
 int ml_sumcheck_compute_polynomial(ml_sumcheck* sc, size_t total_degree, uint8_t previous_sum[16], ml_transcript* t,
@@ -977,7 +1169,7 @@ int ml_sumcheck_compute_polynomial(ml_sumcheck* sc, size_t total_degree, uint8_t
     if (total_degree > 16) { set_error("total_degree too large"); return ML_ERR_ARG; }
     hfe prev = hfe_load(previous_sum), r;
     std::vector<hfe> nz(total_degree ? total_degree : 1);
-    MLB_TRY(sumcheck_round(ctx, sc, total_degree, &prev, t, nz.data(), &r, ctx->stream));
+    MLB_TRY(sumcheck_round(ctx, sc, total_degree, &prev, t, nz.data(), &r, lib_stream(ctx)));
     for (size_t i = 0; i < total_degree; i++) hfe_store(nonzero_coeffs_out + 16 * i, nz[i]);
     hfe_store(previous_sum, prev);
     hfe_store(r_out, r);
@@ -993,11 +1185,11 @@ int ml_sumcheck_compute_polynomials(ml_sumcheck* sc, size_t composition_degree, 
     std::vector<hfe> nz(td);
     for (size_t k = 0; k < rounds; k++) {
         hfe r;
-        MLB_TRY(sumcheck_round(ctx, sc, td, &prev, t, nz.data(), &r, ctx->stream));
+        MLB_TRY(sumcheck_round(ctx, sc, td, &prev, t, nz.data(), &r, lib_stream(ctx)));
         for (size_t i = 0; i < td; i++) hfe_store(coeffs_out + 16 * (k * td + i), nz[i]);
         hfe_store(randoms_out + 16 * k, r);
     }
-    MLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MLB_CUDA(cudaStreamSynchronize(lib_stream(ctx)));
     return ML_OK;
 }
 int ml_delta_evaluate(const uint8_t* data, const uint8_t* points, size_t n, uint8_t out[16]) {
@@ -1018,19 +1210,14 @@ int ml_pcs_prove_dev(const uint8_t* inputs, size_t n_vars, const uint8_t output[
     MLB_TRY(encode_poly(ctx, (const fe*)evals_dev, n, &code, s));  // :101-107
     // PCSProverData::fold (:43-76)
     ml_fri* f;
-    MLB_TRY(fri_init_owned(&f, code, domain, true, t, s));  // :30
+    MLB_TRY(fri_new_unabsorbed(&f, code, domain, true, s));  // :30 (root absorbed on the device by the chain)
     ml_sumcheck* sc = nullptr;
     int st = sumcheck_build(ctx, inputs, n_vars, evals_dev, true, n, s, &sc);  // :31
     ml_pcs_proof* p = new ml_pcs_proof();
     const size_t num_steps = ilog2(domain) - ML_LOG_BLOWUP;  // :52
     p->sumcheck.resize(2 * num_steps);
-    hfe prev = hfe_load(output);
-    for (size_t k = 0; k < num_steps && st == ML_OK; k++) {
-        hfe r;
-        st = sumcheck_round(ctx, sc, 2, &prev, t, &p->sumcheck[2 * k], &r, s);  // :61-66
-        if (st == ML_OK) st = fri_fold_step_impl(ctx, f, k, r, t, s);           // :72
-    }
-    if (st == ML_OK && !f->has_last) { set_error("last_element is None"); st = ML_ERR_SIZE; }
+    // rounds :58-73 — sumcheck polynomial, shared challenge, table fold, FRI fold, commit — without host round trips
+    if (st == ML_OK) st = fold_chain_dev(ctx, f, nullptr, sc, hfe_load(output), p->sumcheck.data(), 0, true, t, s);
     if (st == ML_OK) st = assemble_fri_proof(f, domain, t, &p->fri, s);  // :113-129
     if (st == ML_OK) {
         p->inputs.resize(n_vars);
@@ -1046,7 +1233,7 @@ int ml_pcs_prove_dev(const uint8_t* inputs, size_t n_vars, const uint8_t output[
 int ml_pcs_prove(const uint8_t* inputs, size_t n_vars, const uint8_t output[16], const uint8_t* evals, size_t n, ml_transcript* t,
                  ml_pcs_proof** out) {
     API_BEGIN
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     Scratch d(s);
     MLB_TRY(d.alloc(n * 16));
     MLB_TRY(h2d(d.p, evals, n * 16, s));
@@ -1087,7 +1274,7 @@ int ml_fingerprint(const uint8_t r[16], const uint8_t* coeffs, size_t n, uint8_t
 int ml_batched_fri_prove(const uint8_t* const* codes, size_t n_codes, size_t n, const uint8_t* gen_pows, size_t gen_pows_len,
                          ml_transcript* t, ml_bfri_proof** out) {
     API_BEGIN
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     if (n_codes == 0) { set_error("Codes must not be empty"); return ML_ERR_SIZE; }
     MLB_TRY(check_code_len(n));
     if (gen_pows && gen_pows_len != n) { set_error("gen_pows.len() must equal the domain size"); return ML_ERR_SIZE; }
@@ -1101,14 +1288,8 @@ int ml_batched_fri_prove(const uint8_t* const* codes, size_t n_codes, size_t n, 
         MLB_TRY(h2d(c, codes[j], n * 16, s));
     }
     MLB_TRY(bfri_init(&b, t, s));
-    const size_t num_steps = ilog2(n) - ML_LOG_BLOWUP;  // batched_fri.rs:191
-    hfe r = challenge(t);                               // :194
-    MLB_TRY(bfri_batched_fold_step(ctx, &b, r, t, s));
-    for (size_t k = 1; k < num_steps; k++) {            // :198-201
-        r = challenge(t);
-        MLB_TRY(fri_fold_step_impl(ctx, b.fri, k, r, t, s));
-    }
-    if (!b.fri->has_last) { set_error("last_element is None"); return ML_ERR_SIZE; }
+    // batched first fold (:193-195) + the remaining fold steps (:198-201), transcript advanced on the device
+    MLB_TRY(fold_chain_dev(ctx, b.fri, &b, nullptr, 0, nullptr, 0, false, t, s));
     ml_bfri_proof* p = new ml_bfri_proof();
     int st = bfri_assemble(&b, t, p, s);
     if (st != ML_OK) { delete p; return st; }
@@ -1180,13 +1361,7 @@ int ml_batched_pcs_prove_dev(const uint8_t* inputs, size_t n_vars, const uint8_t
     const size_t num_steps = ilog2(domain) - ML_LOG_BLOWUP;  // :90
     p->sumcheck.resize(2 * num_steps);
     hfe prev = fingerprint_host(fr, outs.data(), n_polys);   // :92-94
-    for (size_t k = 0; k < num_steps && st == ML_OK; k++) {  // :100-123
-        hfe r;
-        st = sumcheck_round(ctx, sc, 2, &prev, t, &p->sumcheck[2 * k], &r, s);
-        if (st != ML_OK) break;
-        st = k == 0 ? bfri_batched_fold_step(ctx, &b, r, t, s) : fri_fold_step_impl(ctx, b.fri, k, r, t, s);
-    }
-    if (st == ML_OK && !b.fri->has_last) { set_error("last_element is None"); st = ML_ERR_SIZE; }
+    if (st == ML_OK) st = fold_chain_dev(ctx, b.fri, &b, sc, prev, p->sumcheck.data(), 0, false, t, s);  // :100-123
     if (st == ML_OK) st = bfri_assemble(&b, t, &p->fri, s);  // :155-173
     free_sumcheck(sc);
     if (st != ML_OK) { delete p; return st; }
@@ -1198,7 +1373,7 @@ int ml_batched_pcs_prove_dev(const uint8_t* inputs, size_t n_vars, const uint8_t
 int ml_batched_pcs_prove(const uint8_t* inputs, size_t n_vars, const uint8_t* outputs, size_t n_polys, const uint8_t* const* evals, size_t n,
                          ml_transcript* t, ml_bpcs_proof** out) {
     API_BEGIN
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = lib_stream(ctx);
     std::vector<void*> dev(n_polys, nullptr);
     int st = ML_OK;
     for (size_t j = 0; j < n_polys && st == ML_OK; j++) {

@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const fe* __restri
         if (threadIdx.x == 0) fe_store(out + c, a);
     }
 }
-__global__ void __launch_bounds__(256) sumcheck_fold_kernel(fe* __restrict__ m, fe* __restrict__ d, size_t off, fe r) {
+__global__ void __launch_bounds__(256) sumcheck_fold_kernel(fe* __restrict__ m, fe* __restrict__ d, size_t off, fe r, const fe* __restrict__ r_dev) {
+    if (r_dev) r = fe_load(r_dev);
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < off; i += stride) {
@@ -90,6 +91,16 @@ static int fetch(const fe* dev, int count, hfe* out, cudaStream_t s) {
     return ML_OK;
 }
 
+int sumcheck_max_blocks() { return SC_MAX_BLOCKS; }
+int sumcheck_sums_partials_launch(const fe* m, const fe* d, size_t height, fe* partials, int* n_blocks, cudaStream_t s) {
+    const size_t off = height >> 1;
+    const unsigned nb = blocks_for(off);
+    ProfScope prof(PROF_SUMCHECK_SUMS, 32.0 * (double)height, s);
+    sumcheck_sums_kernel<<<nb, SC_THREADS, 0, s>>>(m, d, off, partials);
+    MLB_KERNEL_CHECK();
+    *n_blocks = (int)nb;
+    return ML_OK;
+}
 int sumcheck_sums_launch(Ctx* ctx, const fe* m, const fe* d, size_t height, hfe* s1, hfe* s2, cudaStream_t s) {
     (void)ctx;
     const size_t off = height >> 1;
@@ -122,11 +133,11 @@ int sumcheck_partial_sum_launch(Ctx* ctx, const fe* m, const fe* d, size_t heigh
     MLB_TRY(dev_free_async(partials, s));
     return ML_OK;
 }
-int sumcheck_fold_launch(fe* m, fe* d, size_t height, hfe r, cudaStream_t s) {
+int sumcheck_fold_launch(fe* m, fe* d, size_t height, hfe r, const fe* r_dev, cudaStream_t s) {
     const size_t off = height >> 1;
     if (off == 0) return ML_OK;
     ProfScope prof(PROF_SUMCHECK_FOLD, 48.0 * (double)height, s);  // read 2 tables (h), write 2 half tables
-    sumcheck_fold_kernel<<<blocks_for(off), 256, 0, s>>>(m, d, off, to_dev_fe_h(r));
+    sumcheck_fold_kernel<<<blocks_for(off), 256, 0, s>>>(m, d, off, to_dev_fe_h(r), r_dev);
     MLB_KERNEL_CHECK();
     return ML_OK;
 }
