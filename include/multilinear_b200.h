@@ -234,6 +234,10 @@ int ml_bpcs_proof_sumcheck_coeffs(const ml_bpcs_proof *p, uint8_t *out);
  * Writes the subtree root of the range (leaf_count a power of two); ranks then all-gather the roots
  * and call ml_merkle_top_from_roots. */
 int ml_batched_leaf_subtree_dev(const void *const *pairs_dev, size_t n_codes, size_t leaf_count, void *stream, uint8_t root_out[32]);
+/* pairs (code[i], code[i+n/2]) of one local code written in exchange order [dest rank][local poly][row][32 B] */
+int ml_pack_pairs_dev(const void *code_dev, size_t n_code, size_t n_ranks, size_t n_local_polys, size_t local_index, void *out_dev, void *stream);
+/* to_coefficient + bit_reverse + reed_solomon of one polynomial given by evaluations (batched_pcs.rs:144-149); code_dev holds 2n elements */
+int ml_pcs_encode_dev(const void *evals_dev, size_t n, void *code_dev, void *stream);
 int ml_merkle_top_from_roots(const uint8_t *roots, size_t n_roots, uint8_t root_out[32]);
 
 /* ---- instrumentation for bench.py ----

@@ -1432,6 +1432,42 @@ int ml_batched_leaf_subtree_dev(const void* const* pairs_dev, size_t n_codes, si
     const int top = (int)ilog2(leaf_count);
     return d2h_sync(root_out, dig.as<uint8_t>() + 32 * merkle_layer_offset(leaf_count, top), 32, s);
 }
+// ReedSolomonPairs of a code, laid out for the leaf-range exchange: pair i of local polynomial `pl` goes to
+// out[((dest * n_local + pl) * rows + i % rows) * 32], dest = i / rows, rows = (n_code / 2) / n_ranks
+__global__ void pack_pairs_kernel(const fe* __restrict__ code, size_t half, size_t rows, size_t n_local, size_t pl, uint4* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < half; i += stride) {
+        const size_t dest = i / rows, r = i - dest * rows;
+        uint4* o = out + 2 * ((dest * n_local + pl) * rows + r);
+        o[0] = *reinterpret_cast<const uint4*>(code + i);
+        o[1] = *reinterpret_cast<const uint4*>(code + i + half);
+    }
+}
+int ml_pack_pairs_dev(const void* code_dev, size_t n_code, size_t n_ranks, size_t n_local_polys, size_t local_index, void* out_dev,
+                      void* stream) {
+    API_BEGIN
+    (void)ctx;
+    const size_t half = n_code / 2;
+    if (!is_pow2(n_code) || n_ranks == 0 || half % n_ranks != 0 || local_index >= n_local_polys) { set_error("ml_pack_pairs_dev: bad partition"); return ML_ERR_SIZE; }
+    size_t blocks = (half + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_pairs_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>((const fe*)code_dev, half, half / n_ranks, n_local_polys, local_index, (uint4*)out_dev);
+    MLB_KERNEL_CHECK();
+    return ML_OK;
+}
+// evals -> to_coefficient -> bit_reverse -> reed_solomon into a caller-provided code buffer (batched_pcs.rs:144-149)
+int ml_pcs_encode_dev(const void* evals_dev, size_t n, void* code_dev, void* stream) {
+    API_BEGIN
+    cudaStream_t s = ST(stream);
+    if (!is_pow2(n)) { set_error("evals length must be a power of two"); return ML_ERR_NOT_POW2; }
+    Scratch coeffs(s), rev(s);
+    MLB_TRY(coeffs.alloc(n * 16));
+    MLB_TRY(rev.alloc(n * 16));
+    MLB_TRY(mobius_launch((const fe*)evals_dev, coeffs.as<fe>(), n, true, s));
+    MLB_TRY(bit_reverse_launch(coeffs.p, rev.p, n, 16, s));
+    return ntt_launch(ctx, rev.as<fe>(), (fe*)code_dev, (int)ilog2(n) + ML_LOG_BLOWUP, false, true, s);
+}
 int ml_merkle_top_from_roots(const uint8_t* roots, size_t n_roots, uint8_t root_out[32]) {
     if (!is_pow2(n_roots)) { set_error("n_roots must be a power of two"); return ML_ERR_NOT_POW2; }
     std::vector<uint8_t> cur(roots, roots + 32 * n_roots), nxt;
