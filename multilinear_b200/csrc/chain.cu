@@ -244,6 +244,59 @@ int chain_last_launch(const fe* two, DevTranscript* tr, fe* last_out, int* statu
     return ML_OK;
 }
 
+// sumcheck-only tail (compute_sumcheck_polynomials, sumcheck.rs:147-172): all remaining rounds of tables with
+// height <= 4096 in one CTA; writes (c1, c2) and r per round
+__global__ void __launch_bounds__(1024, 1) chain_sumcheck_tail_kernel(fe* m, fe* d, size_t height, fe* prev, DevTranscript* trp, fe* sc_out,
+                                                                      fe* r_out) {
+    __shared__ DevTranscript tr;
+    __shared__ fe sh_r, sh_prev, scratch[32];
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    if (tid == 0) { tr = *trp; sh_prev = fe_load(prev); }
+    __syncthreads();
+    int round = 0;
+    for (size_t h = height; h > 1; h >>= 1, round++) {
+        const size_t off = h >> 1;
+        fe_acc s1, s2;
+        acc_zero(s1);
+        acc_zero(s2);
+        for (size_t i = tid; i < off; i += nthreads) {
+            fe m0 = fe_load(m + i), m1 = fe_load(m + i + off), d0 = fe_load(d + i), d1 = fe_load(d + i + off);
+            acc_mul_add(s1, m1, d1);
+            acc_mul_add(s2, fe_sub(fe_add(m1, m1), m0), fe_sub(fe_add(d1, d1), d0));
+        }
+        fe e1 = block_sum(acc_reduce(s1), scratch);
+        fe e2 = block_sum(acc_reduce(s2), scratch);
+        if (tid == 0) {
+            fe e0 = fe_sub(sh_prev, e1);
+            fe c2 = fe_half(fe_add(fe_sub(e0, fe_add(e1, e1)), e2));
+            fe c1 = fe_sub(fe_sub(e1, e0), c2);
+            dt_absorb_fe(&tr, c1);
+            dt_absorb_fe(&tr, c2);
+            fe r = dt_challenge(&tr);
+            sh_prev = fe_add(e0, fe_mul(r, fe_add(c1, fe_mul(r, c2))));
+            fe_store(sc_out + 2 * round, c1);
+            fe_store(sc_out + 2 * round + 1, c2);
+            fe_store(r_out + round, r);
+            sh_r = r;
+        }
+        __syncthreads();
+        const fe r = sh_r;
+        for (size_t i = tid; i < off; i += nthreads) {
+            fe m0 = fe_load(m + i), m1 = fe_load(m + i + off), d0 = fe_load(d + i), d1 = fe_load(d + i + off);
+            fe_store(m + i, fe_add(m0, fe_mul(r, fe_sub(m1, m0))));
+            fe_store(d + i, fe_add(d0, fe_mul(r, fe_sub(d1, d0))));
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { *trp = tr; fe_store(prev, sh_prev); }
+}
+int chain_sumcheck_tail_launch(fe* m, fe* d, size_t height, fe* prev, DevTranscript* tr, fe* sc_out, fe* r_out, cudaStream_t s) {
+    ProfScope prof(PROF_TAIL, 0.0, s);
+    chain_sumcheck_tail_kernel<<<1, 1024, 0, s>>>(m, d, height, prev, tr, sc_out, r_out);
+    MLB_KERNEL_CHECK();
+    return ML_OK;
+}
+
 int chain_challenge_launch(DevTranscript* tr, const uint8_t* absorb, int absorb_len, uint8_t* copy_out, fe* r_out, bool want_challenge,
                            cudaStream_t s) {
     ProfScope prof(PROF_TRANSCRIPT, 0.0, s);

@@ -117,6 +117,9 @@ struct RootTables {
     fe* hi = nullptr;
     fe* lo_ninv = nullptr;
     hfe gen = 0;
+    // inter-pass twiddle matrices of the multi-pass NTT plan for this size: pass_tw[inverse][pass][k*B + b] =
+    // w_N^(+-k*b*A) (times 1/N for pass 0 of the inverse), laid out like the data so the store loop reads it coalesced
+    fe* pass_tw[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
 };
 struct Ctx {
     int device = -1;
@@ -197,6 +200,7 @@ int chain_challenge_launch(DevTranscript* tr, const uint8_t* absorb, int absorb_
 int chain_sumcheck_finish_launch(const fe* partials, int nb, fe* prev, DevTranscript* tr, const uint8_t* absorb, int absorb_len,
                                  uint8_t* copy_out, fe* sc_out, fe* r_out, cudaStream_t s);
 int chain_tail_launch(const TailArgs& a, cudaStream_t s);
+int chain_sumcheck_tail_launch(fe* m, fe* d, size_t height, fe* prev, DevTranscript* tr, fe* sc_out, fe* r_out, cudaStream_t s);
 int chain_last_launch(const fe* two, DevTranscript* tr, fe* last_out, int* status, cudaStream_t s);
 
 }  // namespace mlb

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) mb_field_kernel(fe* out, int iters, fe se
     fe r = fe_add(fe_add(a[0], a[1]), fe_add(a[2], a[3]));
     if (r.v[0] == 0x12345678u && r.v[3] == 0x9abcdef0u) fe_store(out + tid, r);  // keep the chain live
 }
-template <int MODE, int FMA_ADD>  // 0: 32-byte leaf hash, 1: 64-byte node hash; FMA_ADD = add-routing mask
+template <int MODE, int FMA_ADD, int ROT = 0>  // 0: 32-byte leaf hash, 1: 64-byte node hash; FMA_ADD = add-routing mask; ROT = rotation routing
 __global__ void __launch_bounds__(128) mb_sha_kernel(uint32_t* out, int iters, uint32_t seed) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t h[8], g[8];
@@ -42,11 +42,11 @@ __global__ void __launch_bounds__(128) mb_sha_kernel(uint32_t* out, int iters, u
         sha_iv(o);
         if (MODE == 0) {
             uint32_t w[16] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], 0x80000000u, 0u, 0u, 0u, 0u, 0u, 0u, 256u};
-            sha_compress_t<FMA_ADD>(o, w);
+            sha_compress_t<FMA_ADD, ROT>(o, w);
         } else {
             uint32_t w[16] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7]};
-            sha_compress_t<FMA_ADD>(o, w);
-            sha_compress_pad512_t<FMA_ADD>(o);
+            sha_compress_t<FMA_ADD, ROT>(o, w);
+            sha_compress_pad512_t<FMA_ADD, ROT>(o);
         }
 #pragma unroll
         for (int i = 0; i < 8; i++) h[i] = o[i];
@@ -114,6 +114,11 @@ extern "C" int ml_microbench(const char* what, size_t n, int iters, double* ms_o
 #define MB_SHA_VARIANT(M)                                                                                                              \
         else if (w == "sha_leaf_m" #M) mb_sha_kernel<0, M><<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); \
         else if (w == "sha_node_m" #M) mb_sha_kernel<1, M><<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t*)buf, iters, 0x1234567u);
+#define MB_SHA_ROT(M, R)                                                                                                               \
+        else if (w == "sha_leaf_m" #M "_r" #R) mb_sha_kernel<0, M, R><<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); \
+        else if (w == "sha_node_m" #M "_r" #R) mb_sha_kernel<1, M, R><<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t*)buf, iters, 0x1234567u);
+        MB_SHA_ROT(2, 1) MB_SHA_ROT(2, 11) MB_SHA_ROT(2, 111) MB_SHA_ROT(2, 101) MB_SHA_ROT(2, 21) MB_SHA_ROT(2, 121) MB_SHA_ROT(2, 211)
+        MB_SHA_ROT(0, 1) MB_SHA_ROT(0, 11) MB_SHA_ROT(0, 111) MB_SHA_ROT(0, 121) MB_SHA_ROT(2, 221) MB_SHA_ROT(0, 211)
         MB_SHA_VARIANT(0) MB_SHA_VARIANT(63) MB_SHA_VARIANT(3) MB_SHA_VARIANT(1) MB_SHA_VARIANT(2) MB_SHA_VARIANT(19) MB_SHA_VARIANT(11)
         MB_SHA_VARIANT(27) MB_SHA_VARIANT(59) MB_SHA_VARIANT(43)
         else if (w.rfind("pipe", 0) == 0) {

@@ -27,6 +27,7 @@ struct PassArgs {
     const fe* small;  // w_4096^(+-i), i < 2048
     const fe* lo;     // inter-pass twiddle tables of the domain (lo may be the 1/N-scaled copy)
     const fe* hi;
+    const fe* wtab;   // optional precomputed inter-pass twiddle matrix [k*B + b] (saves the table-combine multiply)
     fe scale;         // single-pass inverse: 1/N
     int log_n, log_r, log_t, log_a, log_b;
     int last, inverse, zero_padded, scaled_lo, has_scale;
@@ -34,15 +35,19 @@ struct PassArgs {
     int radix_log[4];
 };
 
-template <int NS>
+// LAST: this round contains the final stages of the tile, where l == 0 for every item, so the twiddle exponent
+// depends on the unrolled j only and the trivial multiplies (w^0) vanish at compile time.  Other rounds multiply
+// unconditionally (tw[0] = 1): a data-dependent skip would put every butterfly in its own basic block and stop
+// the scheduler from interleaving the twelve independent multiply chains of an item.
+template <int NS, bool LAST>
 __device__ __forceinline__ void dif_round(fe* data, const fe* tw, int pitch, int log_r, int log_t, int q, int tid) {
     // stages q .. q+NS-1 of the R-point DIF; an item is the 2^NS elements m = blk*(R>>q) + j*(R>>(q+NS)) + l of column t
-    const int log_lr = log_r - q - NS;  // l range = R >> (q+NS)
+    const int log_lr = LAST ? 0 : log_r - q - NS;  // l range = R >> (q+NS)
     const int items = 1 << (log_r + log_t - NS);
     for (int w = tid; w < items; w += NTT_THREADS) {
         const int t = w & ((1 << log_t) - 1);
         const int rest = w >> log_t;
-        const int l = rest & ((1 << log_lr) - 1);
+        const int l = LAST ? 0 : (rest & ((1 << log_lr) - 1));
         const int blk = rest >> log_lr;
         const int m0 = (blk << (log_r - q)) + l;
         fe x[1 << NS];
@@ -54,11 +59,16 @@ __device__ __forceinline__ void dif_round(fe* data, const fe* tw, int pitch, int
 #pragma unroll
             for (int j = 0; j < (1 << NS); j++) {
                 if (j & span) continue;
-                const int e = (((j & (span - 1)) << log_lr) + l) << (q + u);
                 fe a = x[j], b = x[j + span];
                 x[j] = fe_add(a, b);
                 fe d = fe_sub(a, b);
-                x[j + span] = e ? fe_mul(d, tw[e]) : d;
+                if (LAST) {
+                    if ((j & (span - 1)) != 0) d = fe_mul(d, tw[(j & (span - 1)) << (q + u)]);  // compile-time skip of w^0
+                } else {
+                    const int e = (((j & (span - 1)) << log_lr) + l) << (q + u);
+                    d = fe_mul(d, tw[e]);
+                }
+                x[j + span] = d;
             }
         }
 #pragma unroll
@@ -76,6 +86,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel(PassArgs p) {
     const size_t tile = blockIdx.x;
 
     for (int i = tid; i < (R >> 1); i += NTT_THREADS) tw[i] = fe_load_nc(p.small + ((size_t)i << (12 - p.log_r)));
+    if (tid == 0 && R == 1) tw[0] = fe_one();
 
     // ---- tile coordinates
     size_t a = 0, bt = 0, ap = 0, k0_base = 0;
@@ -95,6 +106,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel(PassArgs p) {
     const int tile_elems = R * T;
     if (!p.last) {
         const size_t base = (a << log_rb) + (bt << p.log_t);
+#pragma unroll 8
         for (int idx = tid; idx < tile_elems; idx += NTT_THREADS) {
             const int t = idx & (T - 1), m = idx >> p.log_t;
             fe v;
@@ -103,6 +115,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel(PassArgs p) {
             data[m * pitch + t] = v;
         }
     } else {
+#pragma unroll 8
         for (int idx = tid; idx < tile_elems; idx += NTT_THREADS) {
             const int m = idx & (R - 1), t = idx >> p.log_r;
             const size_t arow = (((k0_base + t) << log_a_rest) + ap);
@@ -115,11 +128,14 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel(PassArgs p) {
     __syncthreads();
 
     // ---- R-point DIF, three stages per round
+    // the partial round (log_r mod 3 stages) goes first so that the last round is always a full radix-8 one
     for (int q = 0; q < p.log_r;) {
-        const int ns = p.log_r - q >= 3 ? 3 : p.log_r - q;
-        if (ns == 3) dif_round<3>(data, tw, pitch, p.log_r, p.log_t, q, tid);
-        else if (ns == 2) dif_round<2>(data, tw, pitch, p.log_r, p.log_t, q, tid);
-        else dif_round<1>(data, tw, pitch, p.log_r, p.log_t, q, tid);
+        const int rem = p.log_r - q;
+        const int ns = rem % 3 ? rem % 3 : 3;
+        const bool last = rem == ns;
+        if (ns == 3) { if (last) dif_round<3, true>(data, tw, pitch, p.log_r, p.log_t, q, tid); else dif_round<3, false>(data, tw, pitch, p.log_r, p.log_t, q, tid); }
+        else if (ns == 2) { if (last) dif_round<2, true>(data, tw, pitch, p.log_r, p.log_t, q, tid); else dif_round<2, false>(data, tw, pitch, p.log_r, p.log_t, q, tid); }
+        else { if (last) dif_round<1, true>(data, tw, pitch, p.log_r, p.log_t, q, tid); else dif_round<1, false>(data, tw, pitch, p.log_r, p.log_t, q, tid); }
         q += ns;
         __syncthreads();
     }
@@ -133,12 +149,16 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel(PassArgs p) {
             const size_t k = __brev((unsigned)pos) >> (32 - p.log_r);
             const size_t b = (bt << p.log_t) + t;
             fe v = data[pos * pitch + t];
-            size_t e = (k * b) << p.log_a;
-            if (p.inverse) e = (((size_t)1 << p.log_n) - e) & nmask;
-            if (e != 0 || p.scaled_lo) {
-                fe w = fe_load_nc(p.lo + (e & (((size_t)1 << LO_BITS) - 1)));
-                if (e >> LO_BITS) w = fe_mul(w, fe_load_nc(p.hi + (e >> LO_BITS)));
-                v = fe_mul(v, w);
+            if (p.wtab) {
+                v = fe_mul(v, fe_load_nc(p.wtab + (k << p.log_b) + b));
+            } else {
+                size_t e = (k * b) << p.log_a;
+                if (p.inverse) e = (((size_t)1 << p.log_n) - e) & nmask;
+                if (e != 0 || p.scaled_lo) {
+                    fe w = fe_load_nc(p.lo + (e & (((size_t)1 << LO_BITS) - 1)));
+                    if (e >> LO_BITS) w = fe_mul(w, fe_load_nc(p.hi + (e >> LO_BITS)));
+                    v = fe_mul(v, w);
+                }
             }
             fe_store(p.out + base + (k << p.log_b) + t, v);
         }
@@ -182,6 +202,21 @@ __global__ void small_roots_kernel(fe* fwd, fe* inv, fe w, fe winv) {
         fe_store(inv + i, fe_pow_u64(winv, i));
     }
 }
+// inter-pass twiddle matrix: out[k*B + b] = w_N^(+-(k*b) << log_a) (lo may be the 1/N-scaled table)
+__global__ void pass_table_kernel(fe* out, const fe* lo, const fe* hi, int log_n, int log_a, int log_b, int inverse, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t nmask = ((size_t)1 << log_n) - 1;
+    for (; i < count; i += stride) {
+        const size_t k = i >> log_b, b = i & (((size_t)1 << log_b) - 1);
+        size_t e = (k * b) << log_a;
+        if (inverse) e = (((size_t)1 << log_n) - e) & nmask;
+        fe w = fe_load_nc(lo + (e & (((size_t)1 << LO_BITS) - 1)));
+        if (e >> LO_BITS) w = fe_mul(w, fe_load_nc(hi + (e >> LO_BITS)));
+        fe_store(out + i, w);
+    }
+}
+
 // pow_2_generator_powers (src/ntt/mod.rs:18-28): out[i] = hi[i >> LO_BITS] * lo[i & mask]
 __global__ void powers_kernel(fe* out, const fe* lo, const fe* hi, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,6 +266,30 @@ int get_root_tables(Ctx* ctx, int log_n, cudaStream_t s, const RootTables** out)
         it = ctx->roots.emplace(log_n, rt).first;
     }
     *out = &it->second;
+    return ML_OK;
+}
+
+static std::mutex g_pass_table_mu;
+// lazily built, cached per (size, direction, pass); skipped (nullptr) above 1 GiB per table
+static int get_pass_table(Ctx* ctx, int log_n, bool inverse, int pass, int log_a, int log_r, int log_b, cudaStream_t s, const fe** out) {
+    *out = nullptr;
+    const size_t count = (size_t)1 << (log_r + log_b);
+    if (count * 16 > ((size_t)1 << 30)) return ML_OK;
+    std::lock_guard<std::mutex> lock(g_pass_table_mu);
+    RootTables& rt = ctx->roots[log_n];  // exists: get_root_tables ran first
+    fe*& slot = rt.pass_tw[inverse ? 1 : 0][pass];
+    if (!slot) {
+        fe* tab;
+        if (cudaMalloc((void**)&tab, count * 16) != cudaSuccess) { cudaGetLastError(); return ML_OK; }  // fall back to the two-level path
+        size_t blocks = (count + 255) / 256;
+        if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
+        const fe* lo = (inverse && pass == 0) ? rt.lo_ninv : rt.lo;
+        pass_table_kernel<<<(unsigned)blocks, 256, 0, s>>>(tab, lo, rt.hi, log_n, log_a, log_b, inverse ? 1 : 0, count);
+        MLB_KERNEL_CHECK();
+        MLB_CUDA(cudaStreamSynchronize(s));
+        slot = tab;
+    }
+    *out = slot;
     return ML_OK;
 }
 
@@ -287,6 +346,8 @@ int ntt_launch(Ctx* ctx, const fe* in, fe* out, int log_n, bool inverse, bool rs
         a.zero_padded = (rs_zero_padded && p == 0) ? 1 : 0;
         a.scaled_lo = (inverse && p == 0 && n_passes > 1) ? 1 : 0;
         a.lo = a.scaled_lo ? rt->lo_ninv : rt->lo;
+        a.wtab = nullptr;
+        if (!a.last) MLB_TRY(get_pass_table(ctx, log_n, inverse, p, a.log_a, a.log_r, a.log_b, s, &a.wtab));
         a.has_scale = (inverse && n_passes == 1) ? 1 : 0;
         if (a.has_scale) a.scale = to_dev_fe(hfe_inv(hfe_new((hfe)1 << log_n)));
         const int R = 1 << a.log_r, T = 1 << a.log_t;

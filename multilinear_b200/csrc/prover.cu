@@ -1180,16 +1180,52 @@ int ml_sumcheck_compute_polynomials(ml_sumcheck* sc, size_t composition_degree, 
     API_BEGIN
     const size_t td = composition_degree + 1;  // :159
     if (td > 16) { set_error("composition_degree too large"); return ML_ERR_ARG; }
-    hfe prev = hfe_load(sum);
+    cudaStream_t s = lib_stream(ctx);
     const size_t rounds = sc->height ? ilog2(sc->height) : 0;  // :160
-    std::vector<hfe> nz(td);
-    for (size_t k = 0; k < rounds; k++) {
-        hfe r;
-        MLB_TRY(sumcheck_round(ctx, sc, td, &prev, t, nz.data(), &r, lib_stream(ctx)));
-        for (size_t i = 0; i < td; i++) hfe_store(coeffs_out + 16 * (k * td + i), nz[i]);
-        hfe_store(randoms_out + 16 * k, r);
+    if (td != 2) {  // general degree: host transcript, one partial_sum launch per evaluation point
+        hfe prev = hfe_load(sum);
+        std::vector<hfe> nz(td);
+        for (size_t k = 0; k < rounds; k++) {
+            hfe r;
+            MLB_TRY(sumcheck_round(ctx, sc, td, &prev, t, nz.data(), &r, s));
+            for (size_t i = 0; i < td; i++) hfe_store(coeffs_out + 16 * (k * td + i), nz[i]);
+            hfe_store(randoms_out + 16 * k, r);
+        }
+        MLB_CUDA(cudaStreamSynchronize(s));
+        return ML_OK;
     }
-    MLB_CUDA(cudaStreamSynchronize(lib_stream(ctx)));
+    // the PCS degree: every round on the device (transcript in HBM), one synchronisation at the end
+    if (rounds == 0) return ML_OK;
+    const int max_nb = sumcheck_max_blocks();
+    Scratch blk(s);
+    const size_t off_tr = 0, off_r = 128, off_prev = 160, off_sc = 192, off_rs = off_sc + 2 * 64 * 16, off_part = off_rs + 64 * 16,
+                 total = off_part + (size_t)(2 * max_nb + 2) * 16;
+    MLB_TRY(blk.alloc(total));
+    uint8_t* base = blk.as<uint8_t>();
+    DevTranscript* tr_dev = (DevTranscript*)(base + off_tr);
+    fe *r_dev = (fe*)(base + off_r), *prev_dev = (fe*)(base + off_prev), *sc_dev = (fe*)(base + off_sc), *rs_dev = (fe*)(base + off_rs),
+       *partials = (fe*)(base + off_part);
+    MLB_CUDA(cudaMemsetAsync(base, 0, off_part, s));
+    MLB_TRY(h2d(tr_dev, &t->sha, sizeof(DevTranscript), s));
+    MLB_TRY(h2d(prev_dev, sum, 16, s));
+    size_t k = 0;
+    for (; k < rounds && sc->height > ((size_t)1 << TAIL_LOG); k++) {
+        int nb = 0;
+        MLB_TRY(sumcheck_sums_partials_launch(sc->matrix, sc->delta, sc->height, partials, &nb, s));
+        MLB_TRY(chain_sumcheck_finish_launch(partials, nb, prev_dev, tr_dev, nullptr, 0, nullptr, sc_dev + 2 * k, r_dev, s));
+        MLB_CUDA(cudaMemcpyAsync(rs_dev + k, r_dev, 16, cudaMemcpyDeviceToDevice, s));
+        MLB_TRY(sumcheck_fold_launch(sc->matrix, sc->delta, sc->height, 0, r_dev, s));
+        sc->height >>= 1;
+    }
+    if (k < rounds) {
+        MLB_TRY(chain_sumcheck_tail_launch(sc->matrix, sc->delta, sc->height, prev_dev, tr_dev, sc_dev + 2 * k, rs_dev + k, s));
+        sc->height = 1;
+    }
+    std::vector<uint8_t> host(off_part);
+    MLB_TRY(d2h_sync(host.data(), base, off_part, s));
+    memcpy(coeffs_out, host.data() + off_sc, rounds * 32);
+    memcpy(randoms_out, host.data() + off_rs, rounds * 16);
+    memcpy(&t->sha, host.data() + off_tr, sizeof(DevTranscript));
     return ML_OK;
 }
 int ml_delta_evaluate(const uint8_t* data, const uint8_t* points, size_t n, uint8_t out[16]) {

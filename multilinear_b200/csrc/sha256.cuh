@@ -46,6 +46,40 @@ __device__ __forceinline__ uint32_t sha_s1(uint32_t x) { return sha_rotr(x, 17) 
 __device__ __forceinline__ uint32_t sha_ch(uint32_t e, uint32_t f, uint32_t g) { return (e & f) ^ (~e & g); }
 __device__ __forceinline__ uint32_t sha_maj(uint32_t a, uint32_t b, uint32_t c) { return (a & b) ^ (a & c) ^ (b & c); }
 
+// Rotations / shifts on the fma pipe: x * 2^(32-n) as a 64-bit product has x >> n in its high word and
+// x << (32-n) in its low word, so  rotr(x, n) = IMAD(x, 2^(32-n), IMAD.HI(x, 2^(32-n)))  and  x >> n = IMAD.HI(x, 2^(32-n)).
+// The multiplier comes from the constant bank so neither nvcc nor ptxas can turn it back into a funnel shift.
+// This trades 1 alu-pipe instruction for 2 (rotate) or 1 (shift) fma-pipe instructions; the alu pipe is the bound.
+__constant__ uint32_t kShaPow2[33] = {0u,          1u << 31, 1u << 30, 1u << 29, 1u << 28, 1u << 27, 1u << 26, 1u << 25, 1u << 24, 1u << 23, 1u << 22,
+                                      1u << 21, 1u << 20, 1u << 19, 1u << 18, 1u << 17, 1u << 16, 1u << 15, 1u << 14, 1u << 13, 1u << 12,
+                                      1u << 11, 1u << 10, 1u << 9,  1u << 8,  1u << 7,  1u << 6,  1u << 5,  1u << 4,  1u << 3,  1u << 2,
+                                      1u << 1,  1u};  // kShaPow2[n] = 2^(32-n)
+template <int N>
+__device__ __forceinline__ uint32_t sha_shr_fma(uint32_t x) {
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(kShaPow2[N]));
+    return r;
+}
+template <int N>
+__device__ __forceinline__ uint32_t sha_rotr_fma(uint32_t x) {
+    uint32_t r;
+    asm("{\n\t.reg .u32 t;\n\tmul.hi.u32 t, %1, %2;\n\tmad.lo.u32 %0, %1, %2, t;\n\t}" : "=r"(r) : "r"(x), "r"(kShaPow2[N]));
+    return r;
+}
+// NF = how many of the rotations go to the fma pipe (the rest are funnel shifts), SHRF = shift on the fma pipe
+template <int NF> __device__ __forceinline__ uint32_t sha_S0_t(uint32_t x) {
+    return (NF > 0 ? sha_rotr_fma<2>(x) : sha_rotr(x, 2)) ^ (NF > 1 ? sha_rotr_fma<13>(x) : sha_rotr(x, 13)) ^ (NF > 2 ? sha_rotr_fma<22>(x) : sha_rotr(x, 22));
+}
+template <int NF> __device__ __forceinline__ uint32_t sha_S1_t(uint32_t x) {
+    return (NF > 0 ? sha_rotr_fma<6>(x) : sha_rotr(x, 6)) ^ (NF > 1 ? sha_rotr_fma<11>(x) : sha_rotr(x, 11)) ^ (NF > 2 ? sha_rotr_fma<25>(x) : sha_rotr(x, 25));
+}
+template <int NF, int SHRF> __device__ __forceinline__ uint32_t sha_s0_t(uint32_t x) {
+    return (NF > 0 ? sha_rotr_fma<7>(x) : sha_rotr(x, 7)) ^ (NF > 1 ? sha_rotr_fma<18>(x) : sha_rotr(x, 18)) ^ (SHRF ? sha_shr_fma<3>(x) : (x >> 3));
+}
+template <int NF, int SHRF> __device__ __forceinline__ uint32_t sha_s1_t(uint32_t x) {
+    return (NF > 0 ? sha_rotr_fma<17>(x) : sha_rotr(x, 17)) ^ (NF > 1 ? sha_rotr_fma<19>(x) : sha_rotr(x, 19)) ^ (SHRF ? sha_shr_fma<10>(x) : (x >> 10));
+}
+
 __device__ __forceinline__ void sha_iv(uint32_t st[8]) {
     st[0] = MLB_SHA_IV0; st[1] = MLB_SHA_IV1; st[2] = MLB_SHA_IV2; st[3] = MLB_SHA_IV3;
     st[4] = MLB_SHA_IV4; st[5] = MLB_SHA_IV5; st[6] = MLB_SHA_IV6; st[7] = MLB_SHA_IV7;
@@ -67,23 +101,27 @@ __device__ __forceinline__ uint32_t sha_add(uint32_t a, uint32_t b) {
 #endif
 
 // One compression; w[16] holds the block as big-endian words and is clobbered (rolling schedule).
-template <int MASK>
+// ROT = 100 * (big-sigma rotations on the fma pipe, 0..3) + 10 * (small-sigma rotations, 0..2) + (small-sigma shift on fma, 0/1)
+template <int MASK, int ROT = 0>
 __device__ __forceinline__ void sha_compress_t(uint32_t st[8], uint32_t w[16]) {
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll
     for (int i = 0; i < 64; i++) {
         if (i >= 16)
-            w[i & 15] = sha_add<(MASK & 1) != 0>(sha_add<(MASK & 1) != 0>(w[i & 15], sha_s0(w[(i + 1) & 15])),
-                                                 sha_add<(MASK & 1) != 0>(w[(i + 9) & 15], sha_s1(w[(i + 14) & 15])));
+            w[i & 15] = sha_add<(MASK & 1) != 0>(sha_add<(MASK & 1) != 0>(w[i & 15], sha_s0_t<(ROT / 10) % 10, ROT % 10>(w[(i + 1) & 15])),
+                                                 sha_add<(MASK & 1) != 0>(w[(i + 9) & 15], sha_s1_t<(ROT / 10) % 10, ROT % 10>(w[(i + 14) & 15])));
         // h + K + W first: it does not depend on this round's e, so it stays off the critical path
         uint32_t hkw = sha_add<(MASK & 2) != 0>(sha_add<(MASK & 2) != 0>(w[i & 15], kShaK[i]), h);
-        uint32_t t1 = sha_add<(MASK & 4) != 0>(sha_add<(MASK & 4) != 0>(hkw, sha_ch(e, f, g)), sha_S1(e));
-        uint32_t t2 = sha_add<(MASK & 8) != 0>(sha_S0(a), sha_maj(a, b, c));
+        uint32_t t1 = sha_add<(MASK & 4) != 0>(sha_add<(MASK & 4) != 0>(hkw, sha_ch(e, f, g)), sha_S1_t<ROT / 100>(e));
+        uint32_t t2 = sha_add<(MASK & 8) != 0>(sha_S0_t<ROT / 100>(a), sha_maj(a, b, c));
         h = g; g = f; f = e; e = sha_add<(MASK & 16) != 0>(d, t1); d = c; c = b; b = a; a = sha_add<(MASK & 32) != 0>(t1, t2);
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
-__device__ __forceinline__ void sha_compress(uint32_t st[8], uint32_t w[16]) { sha_compress_t<MLB_SHA_ADD_MASK>(st, w); }
+#ifndef MLB_SHA_ROT
+#define MLB_SHA_ROT 1
+#endif
+__device__ __forceinline__ void sha_compress(uint32_t st[8], uint32_t w[16]) { sha_compress_t<MLB_SHA_ADD_MASK, MLB_SHA_ROT>(st, w); }
 
 // Compression over a constant block (the padding block that ends every 64-byte message): the whole message
 // schedule is known at compile time, so round i only needs the immediate K[i] + W[i].
@@ -107,19 +145,19 @@ constexpr ShaKW sha_make_pad_kw(uint32_t message_bits) {
 }
 __device__ static constexpr ShaKW kShaPad512 = sha_make_pad_kw(512u);
 
-template <int MASK>
+template <int MASK, int ROT = 0>
 __device__ __forceinline__ void sha_compress_pad512_t(uint32_t st[8]) {
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll
     for (int i = 0; i < 64; i++) {
         uint32_t hkw = sha_add<(MASK & 2) != 0>(h, kShaPad512.v[i]);
-        uint32_t t1 = sha_add<(MASK & 4) != 0>(sha_add<(MASK & 4) != 0>(hkw, sha_ch(e, f, g)), sha_S1(e));
-        uint32_t t2 = sha_add<(MASK & 8) != 0>(sha_S0(a), sha_maj(a, b, c));
+        uint32_t t1 = sha_add<(MASK & 4) != 0>(sha_add<(MASK & 4) != 0>(hkw, sha_ch(e, f, g)), sha_S1_t<ROT / 100>(e));
+        uint32_t t2 = sha_add<(MASK & 8) != 0>(sha_S0_t<ROT / 100>(a), sha_maj(a, b, c));
         h = g; g = f; f = e; e = sha_add<(MASK & 16) != 0>(d, t1); d = c; c = b; b = a; a = sha_add<(MASK & 32) != 0>(t1, t2);
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
-__device__ __forceinline__ void sha_compress_pad512(uint32_t st[8]) { sha_compress_pad512_t<MLB_SHA_ADD_MASK>(st); }
+__device__ __forceinline__ void sha_compress_pad512(uint32_t st[8]) { sha_compress_pad512_t<MLB_SHA_ADD_MASK, MLB_SHA_ROT>(st); }
 
 // SHA-256 of a 32-byte message given as 8 big-endian words.
 __device__ __forceinline__ void sha256_leaf32(const uint32_t m[8], uint32_t out[8]) {
