@@ -249,6 +249,7 @@ int ml_merkle_top_from_roots(const uint8_t *roots, size_t n_roots, uint8_t root_
 int ml_profile_enable(int on);
 int ml_profile_reset(void);
 int ml_profile_get(int id, double *total_ms, uint64_t *launches, double *alg_bytes);
+int ml_profile_get_max(int id, double *mean_ms, uint64_t *launches, double *alg_bytes); /* the group's largest launches */
 int ml_microbench(const char *what, size_t n, int iters, double *ms_out, double *work_out);
 
 #ifdef __cplusplus

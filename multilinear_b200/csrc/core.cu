@@ -140,6 +140,23 @@ int ml_profile_get(int id, double* total_ms, uint64_t* launches, double* alg_byt
     return ML_OK;
 }
 
+// the largest launches of a group (records whose algorithmic bytes equal the group's maximum): mean device time
+int ml_profile_get_max(int id, double* mean_ms, uint64_t* launches, double* alg_bytes) {
+    MLB_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    double mx = -1;
+    for (auto& r : g_prof)
+        if (r.id == id && r.closed && r.bytes > mx) mx = r.bytes;
+    double ms = 0;
+    uint64_t n = 0;
+    for (auto& r : g_prof) {
+        if (r.id != id || !r.closed || r.bytes != mx) continue;
+        float t = 0;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { ms += t; n++; }
+    }
+    *mean_ms = n ? ms / n : 0; *launches = n; *alg_bytes = mx < 0 ? 0 : mx;
+    return ML_OK;
+}
 int ml_stream_create(void** out) {
     cudaStream_t s;
     MLB_CUDA(cudaStreamCreate(&s));  // blocking stream: ordered against the legacy default stream (event timing in bench.py)

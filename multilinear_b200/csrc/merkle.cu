@@ -32,6 +32,7 @@ __device__ __forceinline__ void subtree_walk(const fe* __restrict__ code, uint8_
                                              size_t first) {
     uint32_t stack[LOG_G > 0 ? LOG_G : 1][8];
     uint32_t h[8];
+    uint4 nx = make_uint4(0, 0, 0, 0), ny = nx;  // second half of the 32-byte sectors fetched for an even leaf
     int j = 0, lvl = -1;  // lvl < 0: next hash is leaf j; otherwise node(stack[lvl], h)
     size_t idx = first;
 #pragma unroll 1
@@ -41,8 +42,21 @@ __device__ __forceinline__ void subtree_walk(const fe* __restrict__ code, uint8_
         if (leaf) {
             idx = first + j;
             if (LEAVES) {
-                sha_words_from_le(__ldg(reinterpret_cast<const uint4*>(code + idx)), w);
-                sha_words_from_le(__ldg(reinterpret_cast<const uint4*>(code + idx + n_leaves)), w + 4);
+                // leaves come in pairs: fetch whole 32-byte sectors (elements idx, idx+1 of each half) once, use the
+                // second element on the next iteration — 16-byte loads re-fetched half-used sectors from DRAM (ncu v2)
+                uint4 x, y;
+                if (LOG_G > 0 && (j & 1)) {
+                    x = nx; y = ny;
+                } else {
+                    x = __ldg(reinterpret_cast<const uint4*>(code + idx));
+                    y = __ldg(reinterpret_cast<const uint4*>(code + idx + n_leaves));
+                    if (LOG_G > 0) {
+                        nx = __ldg(reinterpret_cast<const uint4*>(code + idx + 1));
+                        ny = __ldg(reinterpret_cast<const uint4*>(code + idx + 1 + n_leaves));
+                    }
+                }
+                sha_words_from_le(x, w);
+                sha_words_from_le(y, w + 4);
                 w[8] = 0x80000000u; w[9] = 0; w[10] = 0; w[11] = 0; w[12] = 0; w[13] = 0; w[14] = 0; w[15] = 256u;
             } else {
                 sha_load_digest(layer_ptr(digests, n_leaves, base_layer, idx), h);

@@ -76,11 +76,12 @@ __device__ __forceinline__ void dif_round(fe* data, const fe* tw, int pitch, int
     }
 }
 
-__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel(PassArgs p) {
+__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(PassArgs p) {
     extern __shared__ uint4 smem_raw[];
     fe* data = reinterpret_cast<fe*>(smem_raw);
     const int R = 1 << p.log_r, T = 1 << p.log_t;
-    const int pitch = T > 1 ? T + 1 : 1;
+    // the row padding only matters where lanes run along m (the last pass's contiguous-row load)
+    const int pitch = (p.last && T > 1) ? T + 1 : T;
     fe* tw = data + (size_t)R * pitch;
     const int tid = threadIdx.x;
     const size_t tile = blockIdx.x;
@@ -351,7 +352,7 @@ int ntt_launch(Ctx* ctx, const fe* in, fe* out, int log_n, bool inverse, bool rs
         a.has_scale = (inverse && n_passes == 1) ? 1 : 0;
         if (a.has_scale) a.scale = to_dev_fe(hfe_inv(hfe_new((hfe)1 << log_n)));
         const int R = 1 << a.log_r, T = 1 << a.log_t;
-        const int pitch = T > 1 ? T + 1 : 1;
+        const int pitch = (a.last && T > 1) ? T + 1 : T;
         const size_t smem = ((size_t)R * pitch + (R >> 1) + 1) * 16;
         const size_t tiles = ((size_t)1 << log_n) >> (a.log_r + a.log_t);
         ntt_pass_kernel<<<(unsigned)tiles, NTT_THREADS, smem, s>>>(a);

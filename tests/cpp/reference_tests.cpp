@@ -1,0 +1,137 @@
+// The reference's own unit tests (hot-path subset), re-expressed against the C++ mirror of its interface
+// (include/multilinear_b200.hpp).  Each test cites the Rust test it follows; they are round-trip / prove->verify
+// checks exactly like the originals, plus the golden roots pinned in tests/golden/vectors.json.
+//   build: g++ -std=c++17 -Iinclude tests/cpp/reference_tests.cpp -Lmultilinear_b200 -lmultilinear_b200
+#include <cstdio>
+#include <string>
+
+#include "multilinear_b200.hpp"
+
+using namespace ml;
+
+static int failures = 0;
+#define EXPECT(cond)                                                            \
+    do {                                                                        \
+        if (!(cond)) { printf("  FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); failures++; } \
+    } while (0)
+
+static std::string hex(const HashDigest& d) {
+    static const char* k = "0123456789abcdef";
+    std::string s;
+    for (uint8_t b : d) { s += k[b >> 4]; s += k[b & 15]; }
+    return s;
+}
+static std::vector<std::vector<uint8_t>> bytes1(std::initializer_list<int> v) {
+    std::vector<std::vector<uint8_t>> out;
+    for (int x : v) out.push_back({(uint8_t)x});
+    return out;
+}
+
+// src/ntt/mod.rs:192-201
+static void intt_test() {
+    const int log_n = 18;
+    std::vector<F> coeffs;
+    for (long long i = 0; i < (1 << log_n); i++) coeffs.push_back(F::from(i));
+    Polynomial pol{coeffs};
+    F gen = *pow_2_generator(log_n);
+    LagrangePolynomial ntt = pol.ntt(gen);
+    Polynomial intt = ntt.intt();
+    EXPECT(pol == intt);
+}
+// src/merkle_tree/mod.rs:301-309
+static void merkle_test() {
+    Merkle tree = Merkle::commit(bytes1({0, 8, 4, 1, 5, 7, 6, 1}));
+    auto proof = tree.open(5);
+    EXPECT(proof.has_value());
+    EXPECT(proof->verify(tree.root(), 5) == 0);
+    EXPECT(hex(tree.root()) == "5363442da24fb12a0ccc1648a93f5ffcebfc51f486b4690d52b2c237a8540573");
+    EXPECT(!tree.open(8).has_value());
+    bool panicked = false;
+    try { Merkle::commit(bytes1({1, 2, 3})); } catch (const Panic& p) { panicked = p.code == ML_ERR_NOT_POW2; }
+    EXPECT(panicked);  // assert!(data.len().is_power_of_two())
+}
+// src/merkle_tree/mod.rs:312-351
+static void batched_merkle_test() {
+    Merkle tree = Merkle::batch_commit({bytes1({0, 8, 4, 1, 5, 7, 6, 1}), bytes1({1, 3, 2, 3, 2, 1, 2, 3})});
+    auto proof = tree.batch_open(5);
+    EXPECT(proof->value.size() == 2 && proof->value[0] == 7 && proof->value[1] == 1);
+    EXPECT(proof->verify(tree.root(), 5) == 0);
+    proof = tree.batch_open(2);
+    EXPECT(proof->value[0] == 4 && proof->value[1] == 2);
+    EXPECT(proof->verify(tree.root(), 2) == 0);
+    EXPECT(proof->verify(tree.root(), 1) != 0);  // incorrect index fails
+    EXPECT(hex(tree.root()) == "1abbfb63f271dd7335a2763a6ec1d931745c6a44f9dd659f01081f848e74f44a");
+}
+// src/polynomials.rs:207-214 (length 6: only the first 2^trailing_zeros entries are transformed)
+static void multilinear_conversion_test() {
+    MultilinearPolynomialEvals evals{{F::from(0), F::from(1), F::from(4), F::from(8), F::from(9), F::from(3)}};
+    MultilinearPolynomial pol = evals.to_coefficient();
+    EXPECT(evals == pol.to_evaluation());
+}
+// src/fri/mod.rs:350-363
+static void prove_and_verify_test() {
+    const int log_n = 10;
+    std::vector<F> values;
+    for (long long i = 0; i < (1 << log_n); i++) values.push_back(F::from(i * 7 + 3));
+    std::vector<F> gen_pows = *pow_2_generator_powers(log_n + LOG_BLOWUP);
+    std::vector<F> code = reed_solomon(values, gen_pows[1]);
+    Transcript transcript;
+    FriProof proof = FriProof::prove(code, gen_pows, transcript);
+    EXPECT(proof.verify() == 0);
+    EXPECT(proof.commitments().size() == 10);
+    EXPECT(hex(proof.commitments()[0]) == "f6ea9e052de7f712e802f82ff7ec0f818d484dc56a6e1bc43305acb4026cadf0");
+}
+// src/fri/multilinear_pcs.rs:211-228 — BASELINE config 1
+static void multilinear_pcs_bench_test() {
+    const int n_vars = 20;
+    std::vector<F> evals, inputs;
+    for (long long i = 0; i < (1 << n_vars); i++) evals.push_back(F::from(i * 7 + 3));
+    MultilinearPolynomialEvals multilinear{evals};
+    for (long long i = 0; i < n_vars; i++) inputs.push_back(F::from(i));
+    F output = multilinear.evaluate(inputs);
+    Transcript transcript;
+    PCSProof proof = PCSProof::prove(inputs, output, multilinear, transcript);
+    Transcript vt;
+    EXPECT(proof.verify(vt) == 0);
+    EXPECT(proof.sumcheck_polynomials().size() == (size_t)n_vars);
+}
+// src/fri/batched_pcs.rs:262-306 (n_vars reduced from 20 to 14 to keep the host-side setup short)
+static void batched_pcs_verify_test() {
+    const int n_vars = 14, num_polys = 10;
+    const size_t height = (size_t)1 << n_vars;
+    std::vector<F> inputs;
+    for (long long i = 0; i < n_vars; i++) inputs.push_back(F::from(i));
+    std::vector<MultilinearPolynomialEvals> polys;
+    std::vector<F> outputs;
+    for (int i = 0; i < num_polys; i++) {
+        std::vector<F> evals;
+        for (size_t j = 0; j < height; j++) evals.push_back(F::from((long long)((j * 3 + (size_t)i * 5) % 100)));
+        MultilinearPolynomialEvals m{evals};
+        outputs.push_back(m.evaluate(inputs));
+        polys.push_back(std::move(m));
+    }
+    BatchedPCSClaim claim{inputs, outputs};
+    Transcript transcript;
+    BatchedPCSProof proof = BatchedPCSProof::prove(claim, polys, transcript);
+    Transcript vt;
+    EXPECT(proof.verify(vt) == 0);
+}
+
+int main() {
+    struct { const char* name; void (*fn)(); } tests[] = {
+        {"intt_test", intt_test}, {"merkle_test", merkle_test}, {"batched_merkle_test", batched_merkle_test},
+        {"multilinear_conversion_test", multilinear_conversion_test}, {"prove_and_verify_test", prove_and_verify_test},
+        {"multilinear_pcs_bench_test", multilinear_pcs_bench_test}, {"batched_pcs_verify_test", batched_pcs_verify_test}};
+    for (auto& t : tests) {
+        int before = failures;
+        try {
+            t.fn();
+        } catch (const Panic& p) {
+            printf("  PANIC in %s: %s\n", t.name, p.what());
+            failures++;
+        }
+        printf("test %s ... %s\n", t.name, failures == before ? "ok" : "FAILED");
+    }
+    printf("%s\n", failures ? "FAILED" : "all reference tests passed");
+    return failures ? 1 : 0;
+}

@@ -421,3 +421,13 @@ def test_fullsize_commit_prove_verify_2p22(ml):
     out = ml.MultilinearPolynomialEvals(evals).evaluate(ml.to_ints(inp))
     p = ml.PCSProof.prove(inp, out, evals, ml.Transcript())
     assert p.verify(ml.Transcript()) == 0
+
+
+# ------------------------------------------------------------------ the reference's own tests on the C++ host mirror
+def test_cpp_reference_tests(ml):
+    import subprocess
+    import __graft_entry__ as g
+    exe = g.build_cpp_tests()
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "all reference tests passed" in p.stdout
