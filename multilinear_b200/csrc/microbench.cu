@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(256) mb_pipe_kernel(uint32_t* out, int iters, 
         for (int i = 0; i < 8; i++) {
             if (MODE == 0 || MODE == 5) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i]));
             if (MODE == 1 || MODE == 5 || MODE == 6 || MODE == 9) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(b[i]) : "r"(m), "r"(a[i]));
-            if (MODE == 2 || MODE == 7) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(wd[i]) : "r"(b[i]), "r"(m));
+            if (MODE == 2 || MODE == 7) asm volatile("{\n\t.reg .u32 lo;\n\tcvt.u32.u64 lo, %0;\n\tmad.wide.u32 %0, lo, %1, %0;\n\t}" : "+l"(wd[i]) : "r"(m));
+            if (MODE == 10 || MODE == 11) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(b[i]) : "r"(m));
+            if (MODE == 11) asm volatile("shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(a[i]));
             if (MODE == 3 || MODE == 6 || MODE == 7 || MODE == 8 || MODE == 9) asm volatile("shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(a[i]));
             if (MODE == 4 || MODE == 8 || MODE == 9) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[i]) : "r"(a[i]), "r"(m));
         }
@@ -134,6 +136,8 @@ extern "C" int ml_microbench(const char* what, size_t n, int iters, double* ms_o
                 case 6: mb_pipe_kernel<6><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
                 case 7: mb_pipe_kernel<7><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
                 case 8: mb_pipe_kernel<8><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
+                case 10: mb_pipe_kernel<10><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
+                case 11: mb_pipe_kernel<11><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
                 default: mb_pipe_kernel<9><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
             }
         }
@@ -155,7 +159,7 @@ extern "C" int ml_microbench(const char* what, size_t n, int iters, double* ms_o
     else if (w == "copy") *work_out = 2.0 * (double)n;
     else if (w.rfind("pipe", 0) == 0) {
         const int mode = atoi(what + 4);
-        const int per = mode <= 4 ? 1 : (mode == 9 ? 3 : 2);
+        const int per = (mode <= 4 || mode == 10) ? 1 : (mode == 9 ? 3 : 2);
         *work_out = (double)n * iters * 8 * per;  // thread-instructions
     }
     else *work_out = (double)n * iters;

@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(PassArgs p) {
     if (!p.last) {
         const size_t base = (a << log_rb) + (bt << p.log_t);
         const size_t nmask = ((size_t)1 << p.log_n) - 1;
+#pragma unroll 4
         for (int idx = tid; idx < tile_elems; idx += NTT_THREADS) {
             const int t = idx & (T - 1), pos = idx >> p.log_t;
             const size_t k = __brev((unsigned)pos) >> (32 - p.log_r);
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(PassArgs p) {
             }
         }
         const int log_r0 = p.n_passes > 1 ? p.radix_log[0] : 0;
+#pragma unroll 4
         for (int idx = tid; idx < tile_elems; idx += NTT_THREADS) {
             const int t = idx & (T - 1), pos = idx >> p.log_t;
             const size_t k = p.log_r ? (__brev((unsigned)pos) >> (32 - p.log_r)) : 0;
