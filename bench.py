@@ -376,9 +376,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=24, dest="log_n")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--polys-per-gpu", type=int, default=4, dest="polys_per_gpu",
+    ap.add_argument("--polys-per-gpu", type=int, default=6, dest="polys_per_gpu",
                     help="independent polynomials committed concurrently per GPU (one stream + host thread each)")
-    ap.add_argument("--e2e-polys", type=int, default=4, dest="e2e_polys",
+    ap.add_argument("--e2e-polys", type=int, default=8, dest="e2e_polys",
                     help="concurrent commits in the end-to-end leg (more in flight hides the PCIe copies)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -125,6 +125,7 @@ struct Ctx {
     int device = -1;
     cudaStream_t stream = nullptr;  // library stream for host-pointer entry points
     std::map<int, RootTables> roots;
+    std::mutex roots_mu;  // guards `roots` and the lazily built tables inside it
     fe* small_fwd = nullptr;  // w_4096^i, i < 2048   (in-tile twiddles for every pass radix <= 4096)
     fe* small_inv = nullptr;  // w_4096^-i
     int sm_count = 148;
@@ -140,7 +141,9 @@ int dev_free_async(void* p, cudaStream_t s);
 
 // ------------------------------------------------------------------ kernels (launchers)
 // ntt.cu
-int ntt_launch(Ctx* ctx, const fe* in, fe* out, int log_n, bool inverse, bool rs_zero_padded, cudaStream_t s);
+// bitrev_in: the n live coefficients are stored bit-reversed (PCS encode); fused into pass 0, multi-pass sizes only
+int ntt_launch(Ctx* ctx, const fe* in, fe* out, int log_n, bool inverse, bool rs_zero_padded, cudaStream_t s, bool bitrev_in = false);
+static inline bool ntt_fuses_bitrev(int log_n) { return log_n > 12; }
 int powers_launch(Ctx* ctx, int log_n, fe* out, cudaStream_t s);
 int bit_reverse_launch(const void* in, void* out, size_t n, size_t elem_bytes, cudaStream_t s);
 // field_ops.cu

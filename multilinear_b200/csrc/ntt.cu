@@ -31,6 +31,7 @@ struct PassArgs {
     fe scale;         // single-pass inverse: 1/N
     int log_n, log_r, log_t, log_a, log_b;
     int last, inverse, zero_padded, scaled_lo, has_scale;
+    int bitrev_in;    // pass 0 of a zero-padded transform: input element j is read from in[rev_{log_n-1}(j)]
     int n_passes;
     int radix_log[4];
 };
@@ -105,7 +106,19 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(PassArgs p) {
 
     // ---- load
     const int tile_elems = R * T;
-    if (!p.last) {
+    if (!p.last && p.bitrev_in) {
+        // PCS encode (multilinear_pcs.rs:101-107): x[j] = c[rev_v(j)], j = m*B + b  ->  c[(rev(b) << (log_r-1)) | rev(m)].
+        // For a fixed column b the R/2 live rows are one contiguous 4 KB block of c, so the permutation costs nothing in HBM.
+        const int half_log = p.log_r - 1, half = R >> 1;
+        for (int idx = tid; idx < half * T; idx += NTT_THREADS) {
+            const int t = idx >> half_log, mp = idx & (half - 1);
+            const size_t b = (bt << p.log_t) + t;
+            const size_t rb = p.log_b ? (size_t)(__brevll((unsigned long long)b) >> (64 - p.log_b)) : 0;
+            const int m = half_log ? (int)(__brev((unsigned)mp) >> (32 - half_log)) : 0;
+            data[m * pitch + t] = fe_load_nc(p.in + (rb << half_log) + mp);
+            data[(m + half) * pitch + t] = fe_zero();
+        }
+    } else if (!p.last) {
         const size_t base = (a << log_rb) + (bt << p.log_t);
 #pragma unroll 8
         for (int idx = tid; idx < tile_elems; idx += NTT_THREADS) {
@@ -238,8 +251,7 @@ static fe to_dev_fe(hfe x) {
 }
 
 int get_root_tables(Ctx* ctx, int log_n, cudaStream_t s, const RootTables** out) {
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
+    std::lock_guard<std::mutex> lock(ctx->roots_mu);
     if (!ctx->small_fwd) {
         hfe w;
         hfe_pow2_generator(12, &w);
@@ -272,13 +284,12 @@ int get_root_tables(Ctx* ctx, int log_n, cudaStream_t s, const RootTables** out)
     return ML_OK;
 }
 
-static std::mutex g_pass_table_mu;
 // lazily built, cached per (size, direction, pass); skipped (nullptr) above 1 GiB per table
 static int get_pass_table(Ctx* ctx, int log_n, bool inverse, int pass, int log_a, int log_r, int log_b, cudaStream_t s, const fe** out) {
     *out = nullptr;
     const size_t count = (size_t)1 << (log_r + log_b);
     if (count * 16 > ((size_t)1 << 30)) return ML_OK;
-    std::lock_guard<std::mutex> lock(g_pass_table_mu);
+    std::lock_guard<std::mutex> lock(ctx->roots_mu);
     RootTables& rt = ctx->roots[log_n];  // exists: get_root_tables ran first
     fe*& slot = rt.pass_tw[inverse ? 1 : 0][pass];
     if (!slot) {
@@ -310,7 +321,8 @@ int powers_launch(Ctx* ctx, int log_n, fe* out, cudaStream_t s) {
 // Natural-order NTT of size 2^log_n with the domain generator pow_2_generator(log_n) (or its inverse, with the
 // 1/N scaling of intt).  rs_zero_padded: `in` holds N/2 coefficients, the upper half of the input is zero
 // (reed_solomon's resize, src/fri/mod.rs:24).  in == out is allowed for P == 1 only when not zero padded.
-int ntt_launch(Ctx* ctx, const fe* in, fe* out, int log_n, bool inverse, bool rs_zero_padded, cudaStream_t s) {
+int ntt_launch(Ctx* ctx, const fe* in, fe* out, int log_n, bool inverse, bool rs_zero_padded, cudaStream_t s, bool bitrev_in) {
+    if (bitrev_in && !(rs_zero_padded && !inverse && log_n > TILE_LOG)) { set_error("ntt: bit-reversed input needs a multi-pass RS encode"); return ML_ERR_ARG; }
     MLB_CUDA(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     const RootTables* rt;
     MLB_TRY(get_root_tables(ctx, log_n, s, &rt));
@@ -347,6 +359,7 @@ int ntt_launch(Ctx* ctx, const fe* in, fe* out, int log_n, bool inverse, bool rs
         a.log_b = log_n - log_a - a.log_r;
         a.log_t = n_passes == 1 ? 0 : TILE_LOG - a.log_r;
         a.zero_padded = (rs_zero_padded && p == 0) ? 1 : 0;
+        a.bitrev_in = (bitrev_in && p == 0) ? 1 : 0;
         a.scaled_lo = (inverse && p == 0 && n_passes > 1) ? 1 : 0;
         a.lo = a.scaled_lo ? rt->lo_ninv : rt->lo;
         a.wtab = nullptr;

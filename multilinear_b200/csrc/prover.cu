@@ -363,16 +363,23 @@ int sumcheck_build(Ctx* ctx, const uint8_t* inputs, size_t n_vars, const void* e
 }
 
 // evals -> to_coefficient -> bit_reverse -> reed_solomon (multilinear_pcs.rs:101-107): returns a new owned code of 2n elements
-int encode_poly(Ctx* ctx, const fe* evals_dev, size_t n, fe** code_out, cudaStream_t s) {
+// writes the code of one polynomial given by evaluations into `code` (2n elements)
+int encode_into(Ctx* ctx, const fe* evals_dev, size_t n, fe* code, cudaStream_t s) {
     const int log_domain = (int)ilog2(n) + ML_LOG_BLOWUP;
-    Scratch coeffs(s), rev(s);
+    Scratch coeffs(s);
     MLB_TRY(coeffs.alloc(n * 16));
-    MLB_TRY(rev.alloc(n * 16));
     MLB_TRY(mobius_launch(evals_dev, coeffs.as<fe>(), n, true, s));
+    if (ntt_fuses_bitrev(log_domain))  // bit_reverse_permutation (:104) folded into the first NTT pass's addressing
+        return ntt_launch(ctx, coeffs.as<fe>(), code, log_domain, false, true, s, true);
+    Scratch rev(s);
+    MLB_TRY(rev.alloc(n * 16));
     MLB_TRY(bit_reverse_launch(coeffs.p, rev.p, n, 16, s));
+    return ntt_launch(ctx, rev.as<fe>(), code, log_domain, false, true, s);
+}
+int encode_poly(Ctx* ctx, const fe* evals_dev, size_t n, fe** code_out, cudaStream_t s) {
     fe* code;
     MLB_TRY(pmalloc((void**)&code, (n << ML_LOG_BLOWUP) * 16, s));
-    int st = ntt_launch(ctx, rev.as<fe>(), code, log_domain, false, true, s);
+    int st = encode_into(ctx, evals_dev, n, code, s);
     if (st != ML_OK) { pfree(code, s); return st; }
     *code_out = code;
     return ML_OK;
@@ -1495,14 +1502,8 @@ int ml_pack_pairs_dev(const void* code_dev, size_t n_code, size_t n_ranks, size_
 // evals -> to_coefficient -> bit_reverse -> reed_solomon into a caller-provided code buffer (batched_pcs.rs:144-149)
 int ml_pcs_encode_dev(const void* evals_dev, size_t n, void* code_dev, void* stream) {
     API_BEGIN
-    cudaStream_t s = ST(stream);
     if (!is_pow2(n)) { set_error("evals length must be a power of two"); return ML_ERR_NOT_POW2; }
-    Scratch coeffs(s), rev(s);
-    MLB_TRY(coeffs.alloc(n * 16));
-    MLB_TRY(rev.alloc(n * 16));
-    MLB_TRY(mobius_launch((const fe*)evals_dev, coeffs.as<fe>(), n, true, s));
-    MLB_TRY(bit_reverse_launch(coeffs.p, rev.p, n, 16, s));
-    return ntt_launch(ctx, rev.as<fe>(), (fe*)code_dev, (int)ilog2(n) + ML_LOG_BLOWUP, false, true, s);
+    return encode_into(ctx, (const fe*)evals_dev, n, (fe*)code_dev, ST(stream));
 }
 int ml_merkle_top_from_roots(const uint8_t* roots, size_t n_roots, uint8_t root_out[32]) {
     if (!is_pow2(n_roots)) { set_error("n_roots must be a power of two"); return ML_ERR_NOT_POW2; }
