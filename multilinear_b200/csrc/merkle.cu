@@ -17,6 +17,14 @@
 
 namespace mlb {
 
+// 16-byte read-only load that asks L2 to bring in the whole 128-byte line: a thread consumes its 8 leaves' 128 bytes
+// over ~40 us, and without the hint every 32-byte sector request became its own 64-byte DRAM burst (ncu: DRAM reads
+// 1.9x the algorithmic bytes, profiles/r1_ncu_top_kernels_v3.txt)
+__device__ __forceinline__ uint4 ldg_line(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::128B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ uint8_t* layer_ptr(uint8_t* digests, size_t n_leaves, int layer, size_t idx) {
     return digests + 32 * ((2 * n_leaves - ((2 * n_leaves) >> layer)) + idx);
 }
@@ -27,10 +35,14 @@ __device__ __forceinline__ uint8_t* layer_ptr(uint8_t* digests, size_t n_leaves,
 // makes a ~450 KB body that thrashes the instruction cache (ncu: stall_no_instruction dominant, profiles/r1_*).
 // Control flow depends only on (j, lvl), identical for every thread, so there is no divergence; the stack is
 // indexed dynamically and lives in local memory (32 bytes of traffic per 2400-instruction hash).
+static const int MERKLE_THREADS = 128;
 template <int LOG_G, bool LEAVES>
 __device__ __forceinline__ void subtree_walk(const fe* __restrict__ code, uint8_t* __restrict__ digests, size_t n_leaves, int base_layer,
                                              size_t first) {
-    uint32_t stack[LOG_G > 0 ? LOG_G : 1][8];
+    // digest stack in shared memory, [level][word][thread]: conflict-free, dynamically indexed, and no local-memory
+    // traffic (the per-thread local stack spilled through L1/L2 into DRAM: ncu showed 2x the algorithmic reads)
+    __shared__ uint32_t stack_sm[LOG_G > 0 ? LOG_G : 1][8][MERKLE_THREADS];
+    const int tx = threadIdx.x;
     uint32_t h[8];
     uint4 nx = make_uint4(0, 0, 0, 0), ny = nx;  // second half of the 32-byte sectors fetched for an even leaf
     int j = 0, lvl = -1;  // lvl < 0: next hash is leaf j; otherwise node(stack[lvl], h)
@@ -42,17 +54,15 @@ __device__ __forceinline__ void subtree_walk(const fe* __restrict__ code, uint8_
         if (leaf) {
             idx = first + j;
             if (LEAVES) {
-                // leaves come in pairs: fetch whole 32-byte sectors (elements idx, idx+1 of each half) once, use the
-                // second element on the next iteration — 16-byte loads re-fetched half-used sectors from DRAM (ncu v2)
                 uint4 x, y;
                 if (LOG_G > 0 && (j & 1)) {
                     x = nx; y = ny;
                 } else {
-                    x = __ldg(reinterpret_cast<const uint4*>(code + idx));
-                    y = __ldg(reinterpret_cast<const uint4*>(code + idx + n_leaves));
+                    x = ldg_line(code + idx);
+                    y = ldg_line(code + idx + n_leaves);
                     if (LOG_G > 0) {
-                        nx = __ldg(reinterpret_cast<const uint4*>(code + idx + 1));
-                        ny = __ldg(reinterpret_cast<const uint4*>(code + idx + 1 + n_leaves));
+                        nx = ldg_line(code + idx + 1);
+                        ny = ldg_line(code + idx + 1 + n_leaves);
                     }
                 }
                 sha_words_from_le(x, w);
@@ -62,8 +72,15 @@ __device__ __forceinline__ void subtree_walk(const fe* __restrict__ code, uint8_
                 sha_load_digest(layer_ptr(digests, n_leaves, base_layer, idx), h);
             }
         } else {
+            // siblings are written together, 64 contiguous bytes: single 32-byte digest stores turned into
+            // read-modify-write DRAM traffic (ncu: DRAM reads 1.9x the algorithmic bytes before this change)
 #pragma unroll
-            for (int k = 0; k < 8; k++) { w[k] = stack[lvl][k]; w[8 + k] = h[k]; }
+            for (int k = 0; k < 8; k++) { w[k] = stack_sm[lvl][k][tx]; w[8 + k] = h[k]; }
+            if (LEAVES || lvl > 0) {
+                uint8_t* dst = layer_ptr(digests, n_leaves, base_layer + lvl, idx - 1);
+                sha_store_digest(dst, w);
+                sha_store_digest(dst + 32, h);
+            }
         }
         if (LEAVES || !leaf) {
             sha_iv(st);
@@ -71,18 +88,16 @@ __device__ __forceinline__ void subtree_walk(const fe* __restrict__ code, uint8_
             if (!leaf) sha_compress_pad512(st);
 #pragma unroll
             for (int k = 0; k < 8; k++) h[k] = st[k];
-            if (leaf) {
-                sha_store_digest(layer_ptr(digests, n_leaves, base_layer, idx), h);
-            } else {
-                idx >>= 1;
-                sha_store_digest(layer_ptr(digests, n_leaves, base_layer + lvl + 1, idx), h);
-            }
+            if (!leaf) idx >>= 1;
         }
         lvl = leaf ? 0 : lvl + 1;
         if (lvl < LOG_G && ((j >> lvl) & 1)) continue;  // left sibling is waiting on the stack: hash the parent next
         if (lvl < LOG_G) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) stack[lvl][k] = h[k];
+            for (int k = 0; k < 8; k++) stack_sm[lvl][k][tx] = h[k];
+        } else {
+            // top of this thread's subtree (adjacent threads write adjacent digests)
+            if (LEAVES || LOG_G > 0) sha_store_digest(layer_ptr(digests, n_leaves, base_layer + LOG_G, idx), h);
         }
         j++;
         lvl = -1;
