@@ -107,7 +107,8 @@ __device__ __forceinline__ void fe_mul_wide(uint32_t r[8], const fe& a, const fe
 }
 
 // 256-bit value p -> canonical element.  Two folds with 2^128 == c, then one conditional subtract.
-__device__ __forceinline__ fe fe_reduce_wide(const uint32_t p[8]) {
+// v1: multiplies by the two limbs of c (12 wide multiply-adds on the half-rate IMAD.WIDE/IMAD.HI path).
+__device__ __forceinline__ fe fe_reduce_wide_v1(const uint32_t p[8]) {
     uint32_t e0 = p[0], e1 = p[1], e2 = p[2], e3 = p[3], e4, e5, o0, o1, o2, o3, o4;
     const uint32_t c0 = MLB_C0, c1 = MLB_C1;
     // x[0..5] = lo + hi*c
@@ -136,6 +137,54 @@ __device__ __forceinline__ fe fe_reduce_wide(const uint32_t p[8]) {
     asm("add.cc.u32 %0, %0, %4; addc.cc.u32 %1, %1, %5; addc.cc.u32 %2, %2, 0; addc.u32 %3, %3, 0;"
         : "+r"(y0), "+r"(y1), "+r"(y2), "+r"(y3) : "r"(m & c0), "r"(m & c1));
     return fe_new(fe{{y0, y1, y2, y3}});
+}
+
+
+// v2: c = 45*2^40 - 1 = (45*2^8) * 2^32 - 1, so hi*c = ((hi * 11520) << 32) - hi: one 14-bit constant, a whole-limb
+// shift and a subtraction.  5 wide multiplies instead of 12; the fma pipe (IMAD.WIDE at half rate) is what bounds
+// fe_mul, the extra IADD3s ride the alu pipe (model + carry analysis: tools/limb_model.py reduce_wide_v2).
+#define MLB_K45 11520u  // 45 << 8
+__device__ __forceinline__ fe fe_reduce_wide_v2(const uint32_t p[8]) {
+    // a[1..5] = lo[1..3] + ((hi * 11520) << 32), as two carry-chained rows of IMAD.WIDE (even limbs of hi, then odd limbs);
+    // the high halves of the products are < 2^14, so the last madc of each row cannot carry out
+    uint32_t a1 = p[1], a2 = p[2], a3 = p[3], a4, a5, x0, x1, x2, x3, x4, x5;
+    const uint32_t k = MLB_K45;
+    asm("mad.lo.cc.u32 %0, %4, %6, %0; madc.hi.cc.u32 %1, %4, %6, %1; madc.lo.cc.u32 %2, %5, %6, %2; madc.hi.u32 %3, %5, %6, 0;"
+        : "+r"(a1), "+r"(a2), "+r"(a3), "=&r"(a4) : "r"(p[4]), "r"(p[6]), "r"(k));
+    asm("mad.lo.cc.u32 %0, %4, %6, %0; madc.hi.cc.u32 %1, %4, %6, %1; madc.lo.cc.u32 %2, %5, %6, %2; madc.hi.u32 %3, %5, %6, 0;"
+        : "+r"(a2), "+r"(a3), "+r"(a4), "=&r"(a5) : "r"(p[5]), "r"(p[7]), "r"(k));
+    // x[0..5] = lo + (t << 32) - hi  (>= 0 and < 2^174 as an integer, so the final borrow is always clear)
+    asm("sub.cc.u32 %0, %6, %12; subc.cc.u32 %1, %7, %13; subc.cc.u32 %2, %8, %14; subc.cc.u32 %3, %9, %15; subc.cc.u32 %4, %10, 0; subc.u32 %5, %11, 0;"
+        : "=&r"(x0), "=&r"(x1), "=&r"(x2), "=&r"(x3), "=&r"(x4), "=&r"(x5)
+        : "r"(p[0]), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7]));
+    // second fold: (x4 + x5*2^32) < 2^46, times 11520 < 2^60
+    const unsigned long long U = (unsigned long long)x4 * MLB_K45 + ((unsigned long long)(x5 * MLB_K45) << 32);
+    uint32_t b1, b2, b3, k1, y0, y1, y2, y3, k2;
+    asm("add.cc.u32 %0, %4, %7; addc.cc.u32 %1, %5, %8; addc.cc.u32 %2, %6, 0; addc.u32 %3, 0, 0;"
+        : "=&r"(b1), "=&r"(b2), "=&r"(b3), "=&r"(k1) : "r"(x1), "r"(x2), "r"(x3), "r"((uint32_t)U), "r"((uint32_t)(U >> 32)));
+    asm("sub.cc.u32 %0, %5, %9; subc.cc.u32 %1, %6, %10; subc.cc.u32 %2, %7, 0; subc.cc.u32 %3, %8, 0; subc.u32 %4, 0, 0;"
+        : "=&r"(y0), "=&r"(y1), "=&r"(y2), "=&r"(y3), "=&r"(k2) : "r"(x0), "r"(b1), "r"(b2), "r"(b3), "r"(x4), "r"(x5));
+    // k2 = 0 or 0xFFFFFFFF (borrow); the true value v = y + (k1 - borrow) * 2^128 is in [0, 2^128 + 2^107), so it wraps
+    // 2^128 at most once.  z = y + c serves both cases: wrapped (v == y + c mod M, y < 2^107 so z < M and no carry) and
+    // not wrapped (carry out of y + c  <=>  y >= M, and then z = y - M): the result is z if wrapped or carry, else y.
+    uint32_t z0, z1, z2, z3, g;
+    asm("add.cc.u32 %0, %5, %9; addc.cc.u32 %1, %6, %10; addc.cc.u32 %2, %7, 0; addc.cc.u32 %3, %8, 0; addc.u32 %4, %11, %12;"
+        : "=&r"(z0), "=&r"(z1), "=&r"(z2), "=&r"(z3), "=&r"(g)
+        : "r"(y0), "r"(y1), "r"(y2), "r"(y3), "r"(MLB_C0), "r"(MLB_C1), "r"(k1), "r"(k2));
+    // g = k1 + k2 + carry (mod 2^32): k1 + k2 is 0 (no wrap: 0+0 or 1+0xFFFFFFFF) or 1 (wrap), and a wrap excludes a carry
+    return fe{{g ? z0 : y0, g ? z1 : y1, g ? z2 : y2, g ? z3 : y3}};
+}
+#ifndef MLB_REDUCE_V
+#define MLB_REDUCE_V 2
+#endif
+template <int V>
+__device__ __forceinline__ fe fe_reduce_wide_t(const uint32_t p[8]) { return V == 1 ? fe_reduce_wide_v1(p) : fe_reduce_wide_v2(p); }
+__device__ __forceinline__ fe fe_reduce_wide(const uint32_t p[8]) { return fe_reduce_wide_t<MLB_REDUCE_V>(p); }
+template <int V>
+__device__ __forceinline__ fe fe_mul_t(const fe& a, const fe& b) {
+    uint32_t p[8];
+    fe_mul_wide(p, a, b);
+    return fe_reduce_wide_t<V>(p);
 }
 
 __device__ __forceinline__ fe fe_mul(const fe& a, const fe& b) {

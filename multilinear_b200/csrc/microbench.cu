@@ -9,7 +9,7 @@
 
 namespace mlb {
 
-template <int MODE>  // 0: multiply chains, 1: butterfly (mul + add + sub) chains
+template <int MODE, int V = MLB_REDUCE_V>  // 0: multiply chains, 1: butterfly (mul + add + sub) chains; V = reduction variant
 __global__ void __launch_bounds__(256) mb_field_kernel(fe* out, int iters, fe seed) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     fe a[4], w = seed;
@@ -20,9 +20,9 @@ __global__ void __launch_bounds__(256) mb_field_kernel(fe* out, int iters, fe se
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int i = 0; i < 4; i += (MODE == 0 ? 1 : 2)) {
-            if (MODE == 0) a[i] = fe_mul(a[i], w);
+            if (MODE == 0) a[i] = fe_mul_t<V>(a[i], w);
             else {
-                fe v = fe_mul(a[i + 1], w), u = a[i];
+                fe v = fe_mul_t<V>(a[i + 1], w), u = a[i];
                 a[i] = fe_add(u, v);
                 a[i + 1] = fe_sub(u, v);
             }
@@ -31,8 +31,9 @@ __global__ void __launch_bounds__(256) mb_field_kernel(fe* out, int iters, fe se
     fe r = fe_add(fe_add(a[0], a[1]), fe_add(a[2], a[3]));
     if (r.v[0] == 0x12345678u && r.v[3] == 0x9abcdef0u) fe_store(out + tid, r);  // keep the chain live
 }
-template <int MODE, int FMA_ADD, int ROT = 0>  // 0: 32-byte leaf hash, 1: 64-byte node hash; FMA_ADD = add-routing mask; ROT = rotation routing
-__global__ void __launch_bounds__(128) mb_sha_kernel(uint32_t* out, int iters, uint32_t seed) {
+template <int MODE, int FMA_ADD, int ROT = 0, int MINB = 1>  // 0: 32-byte leaf hash, 1: 64-byte node hash; FMA_ADD = add-routing mask; ROT = rotation routing;
+// MINB = min CTAs/SM (forcing 32 registers / full occupancy was measured slower: profiles/r1_sha_add_routing.txt)
+__global__ void __launch_bounds__(128, MINB) mb_sha_kernel(uint32_t* out, int iters, uint32_t seed) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t h[8], g[8];
 #pragma unroll
@@ -111,6 +112,10 @@ extern "C" int ml_microbench(const char* what, size_t n, int iters, double* ms_o
         MLB_CUDA(cudaEventRecord(e0, s));
         if (w == "modmul") mb_field_kernel<0><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((fe*)buf, iters, seed);
         else if (w == "butterfly") mb_field_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((fe*)buf, iters, seed);
+        else if (w == "modmul_v1") mb_field_kernel<0, 1><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((fe*)buf, iters, seed);
+        else if (w == "modmul_v2") mb_field_kernel<0, 2><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((fe*)buf, iters, seed);
+        else if (w == "butterfly_v1") mb_field_kernel<1, 1><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((fe*)buf, iters, seed);
+        else if (w == "butterfly_v2") mb_field_kernel<1, 2><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((fe*)buf, iters, seed);
         else if (w == "sha_leaf") mb_sha_kernel<0, MLB_SHA_ADD_MASK><<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t*)buf, iters, 0x1234567u);
         else if (w == "sha_node") mb_sha_kernel<1, MLB_SHA_ADD_MASK><<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t*)buf, iters, 0x1234567u);
 #define MB_SHA_VARIANT(M)                                                                                                              \
@@ -154,8 +159,8 @@ extern "C" int ml_microbench(const char* what, size_t n, int iters, double* ms_o
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *ms_out = best;
-    if (w == "modmul") *work_out = (double)n * iters * 4;
-    else if (w == "butterfly") *work_out = (double)n * iters * 2;
+    if (w.rfind("modmul", 0) == 0) *work_out = (double)n * iters * 4;
+    else if (w.rfind("butterfly", 0) == 0) *work_out = (double)n * iters * 2;
     else if (w == "copy") *work_out = 2.0 * (double)n;
     else if (w.rfind("pipe", 0) == 0) {
         const int mode = atoi(what + 4);
