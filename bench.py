@@ -143,6 +143,47 @@ def run_reference(args):
     return 0
 
 
+def run_batched_commit(torch, ml, L, dist, world, rank, n_polys, log_n, reps=3):
+    """BASELINE configs[4]: batched commit of n_polys polynomials of 2^log_n evaluations, sharded by polynomial for the
+    encode and by leaf range for the hashing (multilinear_b200/sharded.py).  N > 1: the exchange is the store pass
+    writing through NVLink peer mappings; the only collectives are a barrier and the 32-byte root all-gather.
+    Strong scaling (the batch is fixed); reported beside the headline metric, not as it."""
+    from multilinear_b200.sharded import CudaBackend, sharded_batch_commit
+    if n_polys % world or (1 << log_n) % world:
+        return None
+    n = 1 << log_n
+    be = CudaBackend()
+    mine = []
+    for j in range(rank, n_polys, world):
+        t = torch.empty(16 * n, dtype=torch.uint8, device="cuda")
+        ml.check(L.ml_synthetic_elements_dev(C.c_uint64(5000 + j), C.c_size_t(n), C.c_void_p(t.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        mine.append(t)
+    mode = "p2p" if world > 1 else "serial"
+    launches0 = ml.kernel_launches()
+    root = sharded_batch_commit(mine, n, n_polys, be, dist, mode=mode)  # warm-up: tables, pool, peer mappings
+    per_call = ml.kernel_launches() - launches0
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        root = sharded_batch_commit(mine, n, n_polys, be, dist, mode=mode)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    be.release_peer_buffers()
+    del mine
+    torch.cuda.empty_cache()
+    return {"workload": "batched_commit_%dx2^%d" % (n_polys, log_n), "mode": mode, "ms": ms, "value": n_polys * n / (ms * 1e-3) / 1e6,
+            "unit": UNIT, "scaling": "strong", "root": root.hex(), "launches_per_commit_per_rank": per_call,
+            "exchange": "none" if world == 1 else "pack pass stores pairs into peer HBM over NVLink (CUDA IPC); barrier + 32-byte root all-gather over NCCL"}
+
+
 def run_ours(args):
     import torch
     from multilinear_b200 import api as ml
@@ -288,6 +329,10 @@ def run_ours(args):
     for hp in pinned:
         L.ml_host_free_pinned(hp)
 
+    batched = None
+    if not args.no_batched:
+        batched = run_batched_commit(torch, ml, L, dist, world, rank, args.batched_polys, args.batched_log_n)
+
     # max over ranks
     if dist is not None:
         tt = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
@@ -363,6 +408,8 @@ def run_ours(args):
                     "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "includes": "128 query openings + proof serialisation", "matches_device_run": bool(e2e_ok)},
             "gpu_launches": launches, "clocks": sampler.result(), "kernels": kernels,
         }
+        if batched is not None:
+            line["batched_commit"] = batched
         line.update(extra)
         print(json.dumps(line))
     if dist is not None:
@@ -381,6 +428,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--polys-per-gpu", type=int, default=6, dest="polys_per_gpu",
                     help="independent polynomials committed concurrently per GPU (one stream + host thread each)")
+    ap.add_argument("--no-batched", action="store_true", help="skip the sharded batched-commit leg (BASELINE configs[4])")
+    ap.add_argument("--batched-polys", type=int, default=64, dest="batched_polys")
+    ap.add_argument("--batched-log-n", type=int, default=22, dest="batched_log_n")
     ap.add_argument("--e2e-polys", type=int, default=8, dest="e2e_polys",
                     help="concurrent commits in the end-to-end leg (more in flight hides the PCIe copies)")
     args = ap.parse_args()

@@ -239,6 +239,19 @@ int ml_pack_pairs_dev(const void *code_dev, size_t n_code, size_t n_ranks, size_
 /* to_coefficient + bit_reverse + reed_solomon of one polynomial given by evaluations (batched_pcs.rs:144-149); code_dev holds 2n elements */
 int ml_pcs_encode_dev(const void *evals_dev, size_t n, void *code_dev, void *stream);
 int ml_merkle_top_from_roots(const uint8_t *roots, size_t n_roots, uint8_t root_out[32]);
+/* the subtree root left in device memory (32 bytes at root_dev) for the all-gather, no host round trip */
+int ml_batched_leaf_subtree_root_dev(const void *const *pairs_dev, size_t n_codes, size_t leaf_count, void *root_dev, void *stream);
+/* Exchange fused into the pack pass: pairs of one code stored straight into the leaf-range owners' receive buffers
+ * through NVLink peer mappings (no send buffer, no collective).  peer_bases[g] is rank g's receive buffer
+ * ([global polynomial][row][32 B], rows = n_code/2/n_ranks) as mapped into this process (own buffer for g == rank);
+ * max_ctas bounds the grid so the store pass shares the GPU with the next polynomial's NTT (0 = default). */
+#define ML_MAX_PEERS 16
+int ml_pack_pairs_peer_dev(const void *code_dev, size_t n_code, size_t n_ranks, size_t global_poly, void *const *peer_bases, unsigned max_ctas, void *stream);
+/* peer-visible device buffers (CUDA IPC): owner allocates + publishes the 64-byte handle; peers map / unmap it */
+int ml_ipc_alloc(size_t bytes, void **dev_out, uint8_t handle_out[64]);
+int ml_ipc_open(const uint8_t handle[64], void **dev_out);
+int ml_ipc_close(void *dev);
+int ml_ipc_free(void *dev);
 
 /* ---- instrumentation for bench.py ----
  * ml_profile_*: when enabled, every kernel group is bracketed by CUDA events on its launch stream;

@@ -1499,6 +1499,88 @@ int ml_pack_pairs_dev(const void* code_dev, size_t n_code, size_t n_ranks, size_
     MLB_KERNEL_CHECK();
     return ML_OK;
 }
+// Same pairs written straight into the leaf-range owners' receive buffers over NVLink (peer-mapped pointers): the
+// exchange is fused into the pack pass, no send buffer and no collective.  Pair i goes to rank dest = i / rows at
+// peers.base[dest] + ((poly * rows) + i % rows) * 32, i.e. every rank's buffer is [global poly][row][32 B].
+// Warps walk contiguous 32-byte pairs of one destination, so the NVLink writes are full 128-byte lines.
+struct PeerBases {
+    uint4* base[ML_MAX_PEERS];
+};
+__global__ void pack_pairs_peer_kernel(const fe* __restrict__ code, size_t half, size_t rows, size_t poly, PeerBases peers) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < half; i += stride) {
+        const size_t dest = i / rows, r = i - dest * rows;
+        uint4* o = peers.base[dest] + 2 * (poly * rows + r);
+        o[0] = __ldg(reinterpret_cast<const uint4*>(code + i));
+        o[1] = __ldg(reinterpret_cast<const uint4*>(code + i + half));
+    }
+}
+int ml_pack_pairs_peer_dev(const void* code_dev, size_t n_code, size_t n_ranks, size_t global_poly, void* const* peer_bases, unsigned max_ctas,
+                           void* stream) {
+    API_BEGIN
+    (void)ctx;
+    const size_t half = n_code / 2;
+    if (!is_pow2(n_code) || n_ranks == 0 || n_ranks > ML_MAX_PEERS || half % n_ranks != 0) { set_error("ml_pack_pairs_peer_dev: bad partition"); return ML_ERR_SIZE; }
+    PeerBases pb;
+    for (size_t g = 0; g < ML_MAX_PEERS; g++) pb.base[g] = g < n_ranks ? (uint4*)peer_bases[g] : nullptr;
+    size_t blocks = (half + 255) / 256;
+    const size_t cap = max_ctas ? max_ctas : 148 * 8;
+    if (blocks > cap) blocks = cap;
+    pack_pairs_peer_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>((const fe*)code_dev, half, half / n_ranks, global_poly, pb);
+    MLB_KERNEL_CHECK();
+    return ML_OK;
+}
+// Peer-visible device buffers (CUDA IPC): the owner allocates and publishes a 64-byte handle, peers map it.
+int ml_ipc_alloc(size_t bytes, void** dev_out, uint8_t handle_out[64]) {
+    API_BEGIN
+    (void)ctx;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    void* p = nullptr;
+    MLB_CUDA(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); cudaGetLastError(); return ML_ERR_CUDA; }
+    memcpy(handle_out, &h, 64);
+    *dev_out = p;
+    return ML_OK;
+}
+int ml_ipc_open(const uint8_t handle[64], void** dev_out) {
+    API_BEGIN
+    (void)ctx;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    MLB_CUDA(cudaIpcOpenMemHandle(dev_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return ML_OK;
+}
+int ml_ipc_close(void* dev) {
+    API_BEGIN
+    (void)ctx;
+    MLB_CUDA(cudaIpcCloseMemHandle(dev));
+    return ML_OK;
+}
+int ml_ipc_free(void* dev) {
+    API_BEGIN
+    (void)ctx;
+    MLB_CUDA(cudaFree(dev));
+    return ML_OK;
+}
+// device-to-device variant of ml_batched_leaf_subtree_dev: the 32-byte subtree root stays in HBM (root_dev) so it can
+// feed the NCCL all-gather without a host round trip
+int ml_batched_leaf_subtree_root_dev(const void* const* pairs_dev, size_t n_codes, size_t leaf_count, void* root_dev, void* stream) {
+    API_BEGIN
+    (void)ctx;
+    cudaStream_t s = ST(stream);
+    if (!is_pow2(leaf_count) || n_codes == 0) { set_error("leaf_count must be a power of two"); return ML_ERR_NOT_POW2; }
+    Scratch dig(s), ptrs(s);
+    MLB_TRY(dig.alloc(2 * leaf_count * 32));
+    MLB_TRY(ptrs.alloc(n_codes * sizeof(void*)));
+    MLB_TRY(h2d(ptrs.p, pairs_dev, n_codes * sizeof(void*), s));
+    MLB_TRY(merkle_batched_pairs_launch((const uint8_t* const*)ptrs.p, n_codes, leaf_count, dig.as<uint8_t>(), s));
+    const int top = (int)ilog2(leaf_count);
+    MLB_CUDA(cudaMemcpyAsync(root_dev, dig.as<uint8_t>() + 32 * merkle_layer_offset(leaf_count, top), 32, cudaMemcpyDeviceToDevice, s));
+    return ML_OK;
+}
 // evals -> to_coefficient -> bit_reverse -> reed_solomon into a caller-provided code buffer (batched_pcs.rs:144-149)
 int ml_pcs_encode_dev(const void* evals_dev, size_t n, void* code_dev, void* stream) {
     API_BEGIN

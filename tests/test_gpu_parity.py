@@ -365,13 +365,14 @@ def test_batched_pcs_vs_oracle(ml, oracle, nv, B):
 
 
 # ------------------------------------------------------------------ sharded batched commit (config 5), single GPU
-def test_sharded_batch_commit_single_gpu(ml, oracle):
+@pytest.mark.parametrize("mode", ["serial", "pipelined", "p2p"])
+def test_sharded_batch_commit_single_gpu(ml, oracle, mode):
     import torch
     from multilinear_b200.sharded import CudaBackend, sharded_batch_commit
     n, B = 1 << 10, 5
     polys = [oracle.synthetic(2000 + j, n) for j in range(B)]
     local = [torch.from_numpy(p.reshape(-1).copy()).cuda() for p in polys]
-    root = sharded_batch_commit(local, n, B, CudaBackend(), None)
+    root = sharded_batch_commit(local, n, B, CudaBackend(), None, mode=mode)  # p2p degrades to pipelined on one rank
     g = oracle.pow2_generator(11)
     datas = []
     for p in polys:

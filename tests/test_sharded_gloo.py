@@ -5,6 +5,7 @@ import socket
 import sys
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -55,7 +56,7 @@ def _polys(n, n_polys):
     return [O.synthetic(1000 + j, n) for j in range(n_polys)]
 
 
-def _worker(rank, world, port, n, n_polys, out_q):
+def _worker(rank, world, port, n, n_polys, out_q, mode="serial"):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -63,7 +64,7 @@ def _worker(rank, world, port, n, n_polys, out_q):
     from multilinear_b200.sharded import sharded_batch_commit
     polys = _polys(n, n_polys)
     local = [torch.from_numpy(polys[j].reshape(-1).copy()) for j in range(n_polys) if j % world == rank]
-    root = sharded_batch_commit(local, n, n_polys, OracleBackend(), dist)
+    root = sharded_batch_commit(local, n, n_polys, OracleBackend(), dist, mode=mode)
     out_q.put((rank, root))
     dist.barrier()
     dist.destroy_process_group()
@@ -80,14 +81,15 @@ def _reference_root(n, n_polys):
     return O.merkle_batch_commit(datas).root()
 
 
-def test_sharded_batch_commit_world2_matches_single_process():
+@pytest.mark.parametrize("mode", ["serial", "pipelined"])
+def test_sharded_batch_commit_world2_matches_single_process(mode):
     n, n_polys, world = 256, 6, 2
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, n_polys, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, n_polys, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     results = dict(q.get(timeout=120) for _ in range(world))
@@ -98,9 +100,10 @@ def test_sharded_batch_commit_world2_matches_single_process():
     assert results[0] == results[1] == want
 
 
-def test_sharded_batch_commit_single_rank():
+@pytest.mark.parametrize("mode", ["serial", "pipelined"])
+def test_sharded_batch_commit_single_rank(mode):
     sys.path.insert(0, ROOT)
     from multilinear_b200.sharded import sharded_batch_commit
     n, n_polys = 128, 3
     local = [torch.from_numpy(p.reshape(-1).copy()) for p in _polys(n, n_polys)]
-    assert sharded_batch_commit(local, n, n_polys, OracleBackend(), None) == _reference_root(n, n_polys)
+    assert sharded_batch_commit(local, n, n_polys, OracleBackend(), None, mode=mode) == _reference_root(n, n_polys)
