@@ -300,16 +300,22 @@ def run_ours(args):
         pinned.append(hp)
     e2e_out = [None] * PE
 
+    e2e_phase = [[0.0, 0.0] for _ in range(PE)]  # seconds inside the C-ABI prove call / reading the proof back out
+
     def e2e_worker(j, steps):
         ml.set_device(local_rank)
         ml.check(L.ml_set_thread_stream(streams[j], C.c_int(1)))
         for _ in range(steps):
             t = ml.Transcript()
             h = C.c_void_p()
+            t0 = time.perf_counter()
             ml.check(L.ml_rs_fri_prove(pinned[j], C.c_size_t(n), t.h, C.byref(h)))
+            t1 = time.perf_counter()
             proof = ml.FriProof(h)
             e2e_out[j] = (proof.commitments, proof.last_elem, len(proof.serialize()))
             del proof
+            e2e_phase[j][0] += t1 - t0
+            e2e_phase[j][1] += time.perf_counter() - t1
 
     def e2e_run(steps):
         ts = [threading.Thread(target=e2e_worker, args=(j, steps)) for j in range(PE)]
@@ -318,7 +324,27 @@ def run_ours(args):
         for t in ts:
             t.join()
 
+    # raw pinned host -> device bandwidth of this box (explains the e2e figure: 256 MiB of coefficients per commit)
+    h2d_gbs = None
+    try:
+        scratch = ml.DeviceBuffer(16 * n)
+        hb0, hb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = None
+        for _ in range(3):
+            torch.cuda.synchronize()
+            hb0.record()
+            ml.check(L.ml_dev_upload(scratch.ptr, pinned[0], C.c_size_t(16 * n)))
+            hb1.record()
+            torch.cuda.synchronize()
+            dt = hb0.elapsed_time(hb1)
+            best = dt if best is None or dt < best else best
+        h2d_gbs = 16 * n / (best * 1e-3) / 1e9
+        del scratch
+    except Exception:  # noqa: BLE001
+        pass
     e2e_run(1)  # warm-up
+    for ph in e2e_phase:
+        ph[0] = ph[1] = 0.0
     barrier()
     t0 = time.perf_counter()
     e2e_run(e2e_steps)
@@ -405,7 +431,9 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": world * PE * n / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 16 * n * PE, "d2h_bytes_per_step": blob_len * PE,
                     "polys_in_flight": PE,
-                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "includes": "128 query openings + proof serialisation", "matches_device_run": bool(e2e_ok)},
+                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "includes": "128 query openings + proof serialisation", "matches_device_run": bool(e2e_ok),
+                    "pinned_h2d_gbs": h2d_gbs, "prove_call_ms_mean": 1e3 * sum(p[0] for p in e2e_phase) / (PE * e2e_steps),
+                    "proof_readout_ms_mean": 1e3 * sum(p[1] for p in e2e_phase) / (PE * e2e_steps)},
             "gpu_launches": launches, "clocks": sampler.result(), "kernels": kernels,
         }
         if batched is not None:

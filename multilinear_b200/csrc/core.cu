@@ -1,4 +1,5 @@
 // Context, memory and the array-level C ABI (field vectors, NTT, Reed-Solomon, multilinear transforms, transcript).
+#include <cstdlib>
 #include "field.cuh"
 #include "handles.h"
 #include "internal.h"
@@ -67,6 +68,12 @@ int get_ctx(Ctx** out) {
         MLB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
         unsigned long long thr = ~0ull;  // keep freed scratch cached in the pool
         MLB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        // Never satisfy an allocation on one stream with a block whose free is still queued on another stream: the driver
+        // does that by making the allocating stream wait for the other stream's pending work, which silently serialises
+        // concurrent commits (measured: 8 host-pointer commits in flight took 75-1000 ms per step depending on which
+        // block the allocator picked).  Completed frees are still reused; otherwise the pool grows.
+        int off = 0;
+        if (!getenv("MLB_POOL_INTERNAL_DEPS")) MLB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
         it = g_ctx.emplace(dev, c).first;
     }
     *out = it->second;

@@ -5,7 +5,8 @@
 // with the inverse twiddle read from a 512 MiB gen_pows table as gen_pows[N0 - i*2^k] (:106-110).
 // Here the twiddle comes from the two-level root tables already resident for the NTT (one extra multiply,
 // no large-table gather), the challenge is pre-halved on the host (r/2), and the halving of (a + b) is a
-// shift: 3 multiplies, 48 bytes of HBM traffic per output.
+// shift: 3 multiplies, 48 bytes of HBM traffic per output.  The large rounds use fri_fold_chunk_kernel, which folds the
+// high-table factor of the twiddle and r/2 into one constant per 4096-exponent chunk: 2 multiplies per output.
 #include "field.cuh"
 #include "internal.h"
 
@@ -34,6 +35,44 @@ __global__ void __launch_bounds__(256) fri_fold_kernel(const fe* __restrict__ cu
     }
 }
 
+// Two multiplies per output.  With j = i << k:  w^-j = w^-(4096 c) * w^-x,  c = j >> 12, x = j & 4095, and
+//   w^-(4096 c) = hi[H - c] (c > 0),   w^-x = lo[4096 - x] * hi[H - 1] (x > 0),   H = N0 / 4096,
+// so  (r/2) * w^-j = C[c] * lo[(4096 - x) & 4095]  with one constant C per chunk c (times hi[H-1] when x > 0).
+// A CTA owns FOLD_SPAN consecutive outputs = 2^k chunks; its first 2^k threads build the chunk constants in shared
+// memory (2 multiplies each), then every output costs  t = (a - b) * lo[..]  and  C * t.
+static const int FOLD_SPAN = 4096;
+static const int FOLD_MAX_K = 8;  // 2^k chunk constants per CTA <= blockDim
+__global__ void __launch_bounds__(256) fri_fold_chunk_kernel(const fe* __restrict__ cur, size_t half_n, fe* __restrict__ next, fe r_half,
+                                                             const fe* __restrict__ r_dev, int k, int log_n0, const fe* __restrict__ lo,
+                                                             const fe* __restrict__ hi) {
+    __shared__ fe c0[1 << FOLD_MAX_K], c1[1 << FOLD_MAX_K];
+    if (r_dev) r_half = fe_load(r_dev + 1);
+    const int tid = threadIdx.x;
+    const size_t i0 = (size_t)blockIdx.x * FOLD_SPAN;
+    const int log_chunk = LO_BITS - k;  // outputs per chunk
+    const size_t c_first = i0 >> log_chunk;
+    const size_t H = (size_t)1 << (log_n0 - LO_BITS);
+    if (tid < (1 << k)) {
+        const size_t c = c_first + tid;  // c < H / 2 because j < N0 / 2
+        fe base = c ? fe_mul(r_half, fe_load_nc(hi + (H - c))) : r_half;
+        c0[tid] = base;
+        c1[tid] = fe_mul(base, fe_load_nc(hi + (H - 1)));
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int u = 0; u < FOLD_SPAN / 256; u++) {
+        const size_t i = i0 + tid + 256 * u;
+        if (i >= half_n) break;
+        fe a = fe_load_nc(cur + i), b = fe_load_nc(cur + i + half_n);
+        fe even = fe_half(fe_add(a, b));
+        const unsigned x = (unsigned)((i << k) & (((size_t)1 << LO_BITS) - 1));
+        const int ci = (int)((i >> log_chunk) - c_first);
+        fe t = fe_mul(fe_sub(a, b), fe_load_nc(lo + ((((unsigned)1 << LO_BITS) - x) & (((unsigned)1 << LO_BITS) - 1))));  // lo[0] = 1 when x = 0
+        fe c = x ? c1[ci] : c0[ci];
+        fe_store(next + i, fe_add(even, fe_mul(c, t)));
+    }
+}
+
 static fe to_dev_fe(hfe x) {
     fe r;
     r.v[0] = (uint32_t)x; r.v[1] = (uint32_t)(x >> 32); r.v[2] = (uint32_t)(x >> 64); r.v[3] = (uint32_t)(x >> 96);
@@ -51,7 +90,11 @@ int fri_fold_launch(Ctx* ctx, const fe* cur, size_t n_cur, fe* next, hfe r, cons
     MLB_TRY(get_root_tables(ctx, log_n0, s, &rt));
     const size_t half_n = n_cur / 2;
     ProfScope prof(PROF_FRI_FOLD, 24.0 * (double)n_cur, s);  // read n elements, write n/2
-    fri_fold_kernel<<<grid_for(half_n), 256, 0, s>>>(cur, half_n, next, to_dev_fe(hfe_half(r)), r_dev, (int)k, log_n0, rt->lo, rt->hi);
+    if ((int)k <= FOLD_MAX_K && log_n0 > LO_BITS && half_n >= (size_t)FOLD_SPAN && (half_n << k) <= ((size_t)1 << (log_n0 - 1)))
+        fri_fold_chunk_kernel<<<(unsigned)((half_n + FOLD_SPAN - 1) / FOLD_SPAN), 256, 0, s>>>(cur, half_n, next, to_dev_fe(hfe_half(r)), r_dev, (int)k,
+                                                                                                 log_n0, rt->lo, rt->hi);
+    else
+        fri_fold_kernel<<<grid_for(half_n), 256, 0, s>>>(cur, half_n, next, to_dev_fe(hfe_half(r)), r_dev, (int)k, log_n0, rt->lo, rt->hi);
     MLB_KERNEL_CHECK();
     return ML_OK;
 }

@@ -173,6 +173,7 @@ int fingerprint_rows_launch(const fe* const* polys_dev_ptrs, size_t n_polys, siz
 int sumcheck_sums_launch(Ctx* ctx, const fe* m, const fe* d, size_t height, hfe* s1, hfe* s2, cudaStream_t s);
 int sumcheck_partial_sum_launch(Ctx* ctx, const fe* m, const fe* d, size_t height, hfe r, hfe* out, cudaStream_t s);
 int sumcheck_fold_launch(fe* m, fe* d, size_t height, hfe r, const fe* r_dev, cudaStream_t s);
+int sumcheck_fold_sums_launch(fe* m, fe* d, size_t height, const fe* r_dev, fe* partials /* 2 per CTA */, int* n_blocks, cudaStream_t s);
 int sumcheck_sums_partials_launch(const fe* m, const fe* d, size_t height, fe* partials /* 2 per CTA */, int* n_blocks, cudaStream_t s);
 int sumcheck_max_blocks();
 // chain.cu — device-resident transcript steps and the fused tail of the fold chain

@@ -451,7 +451,8 @@ int fold_chain_dev(Ctx* ctx, ml_fri* f, BatchedFri* b, ml_sumcheck* sc, hfe prev
     MLB_TRY(get_root_tables(ctx, f->log_n0, s, &rt));
 
     const size_t first_new_layer = f->layers.size() - (pending ? 1 : 0);  // roots to fetch afterwards: layers >= this index
-    bool used_tail = false;
+    bool used_tail = false, have_partials = false;
+    int sc_nb = 0;
     size_t k = k_start;
     for (; k < total_steps; k++) {
         const bool batched_round = f->layers.empty();
@@ -494,10 +495,13 @@ int fold_chain_dev(Ctx* ctx, ml_fri* f, BatchedFri* b, ml_sumcheck* sc, hfe prev
         const uint8_t* absorb = pending ? layer_root_ptr(f->layers.back()) : nullptr;
         uint8_t* copy_out = pending ? roots_dev + 32 * (f->layers.size() - 1) : nullptr;
         if (sc) {
-            int nb = 0;
-            MLB_TRY(sumcheck_sums_partials_launch(sc->matrix, sc->delta, sc->height, partials, &nb, s));
-            MLB_TRY(chain_sumcheck_finish_launch(partials, nb, prev_dev, tr_dev, absorb, pending ? 32 : 0, copy_out, sc_dev + 2 * (k - k_start), r_dev, s));
-            MLB_TRY(sumcheck_fold_launch(sc->matrix, sc->delta, sc->height, 0, r_dev, s));
+            if (!have_partials) MLB_TRY(sumcheck_sums_partials_launch(sc->matrix, sc->delta, sc->height, partials, &sc_nb, s));
+            MLB_TRY(chain_sumcheck_finish_launch(partials, sc_nb, prev_dev, tr_dev, absorb, pending ? 32 : 0, copy_out, sc_dev + 2 * (k - k_start), r_dev, s));
+            // the next round's sums are fused into this fold whenever that round runs as separate kernels again
+            // (the tail kernel computes its own sums)
+            have_partials = half_n > ((size_t)1 << TAIL_LOG) && sc->height >= 4 && k + 1 < total_steps;
+            if (have_partials) MLB_TRY(sumcheck_fold_sums_launch(sc->matrix, sc->delta, sc->height, r_dev, partials, &sc_nb, s));
+            else MLB_TRY(sumcheck_fold_launch(sc->matrix, sc->delta, sc->height, 0, r_dev, s));
             sc->height >>= 1;
         } else {
             MLB_TRY(chain_challenge_launch(tr_dev, absorb, pending ? 32 : 0, copy_out, r_dev, true, s));
@@ -1216,12 +1220,16 @@ int ml_sumcheck_compute_polynomials(ml_sumcheck* sc, size_t composition_degree, 
     MLB_TRY(h2d(tr_dev, &t->sha, sizeof(DevTranscript), s));
     MLB_TRY(h2d(prev_dev, sum, 16, s));
     size_t k = 0;
+    bool have_partials = false;
+    int nb = 0;
     for (; k < rounds && sc->height > ((size_t)1 << TAIL_LOG); k++) {
-        int nb = 0;
-        MLB_TRY(sumcheck_sums_partials_launch(sc->matrix, sc->delta, sc->height, partials, &nb, s));
+        if (!have_partials) MLB_TRY(sumcheck_sums_partials_launch(sc->matrix, sc->delta, sc->height, partials, &nb, s));
         MLB_TRY(chain_sumcheck_finish_launch(partials, nb, prev_dev, tr_dev, nullptr, 0, nullptr, sc_dev + 2 * k, r_dev, s));
         MLB_CUDA(cudaMemcpyAsync(rs_dev + k, r_dev, 16, cudaMemcpyDeviceToDevice, s));
-        MLB_TRY(sumcheck_fold_launch(sc->matrix, sc->delta, sc->height, 0, r_dev, s));
+        // round k+1 runs as separate kernels again iff its height is still above the tail size: fuse its sums into this fold
+        have_partials = (sc->height >> 1) > ((size_t)1 << TAIL_LOG) && k + 1 < rounds;
+        if (have_partials) MLB_TRY(sumcheck_fold_sums_launch(sc->matrix, sc->delta, sc->height, r_dev, partials, &nb, s));
+        else MLB_TRY(sumcheck_fold_launch(sc->matrix, sc->delta, sc->height, 0, r_dev, s));
         sc->height >>= 1;
     }
     if (k < rounds) {

@@ -77,6 +77,41 @@ __global__ void __launch_bounds__(256) sumcheck_fold_kernel(fe* __restrict__ m, 
     }
 }
 
+// Fold round k and the partial sums of round k+1 in one pass (SURVEY.md §8d "fused fold + next-round sums"): a thread owns the
+// quad (i, i+q, i+off, i+off+q), q = off/2, of both tables, folds it to the two elements (i, i+q) of the half-height
+// tables (stored in place: no other thread touches this quad) and accumulates round k+1's products from the folded values
+// while they are still in registers.  Per round the tables are read once and the half-height tables written once
+// (48 B per input pair instead of 80), 6 multiplies per quad of which 2 stay unreduced in the 288-bit accumulators.
+__global__ void __launch_bounds__(SC_THREADS) sumcheck_fold_sums_kernel(fe* __restrict__ m, fe* __restrict__ d, size_t off,
+                                                                        const fe* __restrict__ r_dev, fe* __restrict__ partials) {
+    __shared__ fe scratch[32];
+    const fe r = fe_load(r_dev);
+    const size_t q = off >> 1;
+    fe_acc a1, a2;
+    acc_zero(a1);
+    acc_zero(a2);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < q; i += stride) {
+        fe m00 = fe_load(m + i), m01 = fe_load(m + i + q), m10 = fe_load(m + i + off), m11 = fe_load(m + i + off + q);
+        fe d00 = fe_load(d + i), d01 = fe_load(d + i + q), d10 = fe_load(d + i + off), d11 = fe_load(d + i + off + q);
+        fe m0 = fe_add(m00, fe_mul(r, fe_sub(m10, m00))), m1 = fe_add(m01, fe_mul(r, fe_sub(m11, m01)));
+        fe d0 = fe_add(d00, fe_mul(r, fe_sub(d10, d00))), d1 = fe_add(d01, fe_mul(r, fe_sub(d11, d01)));
+        fe_store(m + i, m0);
+        fe_store(m + i + q, m1);
+        fe_store(d + i, d0);
+        fe_store(d + i + q, d1);
+        acc_mul_add(a1, m1, d1);
+        acc_mul_add(a2, fe_sub(fe_add(m1, m1), m0), fe_sub(fe_add(d1, d1), d0));
+    }
+    fe s1 = block_sum(acc_reduce(a1), scratch);
+    fe s2 = block_sum(acc_reduce(a2), scratch);
+    if (threadIdx.x == 0) {
+        fe_store(partials + 2 * blockIdx.x, s1);
+        fe_store(partials + 2 * blockIdx.x + 1, s2);
+    }
+}
+
 static inline unsigned blocks_for(size_t n) {
     size_t b = (n + SC_THREADS - 1) / SC_THREADS;
     if (b > (size_t)SC_MAX_BLOCKS) b = SC_MAX_BLOCKS;
@@ -131,6 +166,17 @@ int sumcheck_partial_sum_launch(Ctx* ctx, const fe* m, const fe* d, size_t heigh
     MLB_KERNEL_CHECK();
     MLB_TRY(fetch(partials + nb, 1, out, s));
     MLB_TRY(dev_free_async(partials, s));
+    return ML_OK;
+}
+// fold tables of `height` with the challenge at r_dev and leave round k+1's (e1, e2) partials; needs height >= 4
+int sumcheck_fold_sums_launch(fe* m, fe* d, size_t height, const fe* r_dev, fe* partials, int* n_blocks, cudaStream_t s) {
+    const size_t off = height >> 1;
+    if (off < 2) { set_error("sumcheck_fold_sums: height must be at least 4"); return ML_ERR_SIZE; }
+    const unsigned nb = blocks_for(off >> 1);
+    ProfScope prof(PROF_SUMCHECK_FOLD, 48.0 * (double)height, s);  // read 2 tables (h), write 2 half tables; the sums ride along
+    sumcheck_fold_sums_kernel<<<nb, SC_THREADS, 0, s>>>(m, d, off, r_dev, partials);
+    MLB_KERNEL_CHECK();
+    *n_blocks = (int)nb;
     return ML_OK;
 }
 int sumcheck_fold_launch(fe* m, fe* d, size_t height, hfe r, const fe* r_dev, cudaStream_t s) {
