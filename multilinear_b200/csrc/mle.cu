@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(MLE_THREADS, 2) mobius_pass_kernel(const fe* _
     const size_t hi = tile >> log_runs;
     const size_t base = (hi << (bit_lo + log_r)) + (run << log_t);
     const int tile_elems = R * T;
+    // unrolled so that 8 independent 16-byte loads per thread are in flight (2 CTAs/SM cannot hide HBM latency otherwise)
+#pragma unroll 8
     for (int idx = tid; idx < tile_elems; idx += MLE_THREADS) {
         const int t = idx & (T - 1), m = idx >> log_t;
         data[m * pitch + t] = fe_load_nc(in + base + ((size_t)m << bit_lo) + t);
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(MLE_THREADS, 2) mobius_pass_kernel(const fe* _
         q += ns;
         __syncthreads();
     }
+#pragma unroll 8
     for (int idx = tid; idx < tile_elems; idx += MLE_THREADS) {
         const int t = idx & (T - 1), m = idx >> log_t;
         fe_store(out + base + ((size_t)m << bit_lo) + t, data[m * pitch + t]);
@@ -96,6 +99,8 @@ int mobius_launch(const fe* in, fe* out, size_t len, bool subtract, cudaStream_t
     int bit_lo = 0;
     const fe* src = in;
     // first pass: low min(n,12) bits, contiguous tiles; then groups of <= 8 bits with T = 4096 >> bits columns
+    // later passes take 8 bits each (runs of >= 16 elements = 256 B per row).  Measured alternative: 10 bits with 64-byte runs
+    // saves a pass at v = 22 but that pass runs at half the bandwidth, no net gain (tools/mobius_bench.py)
     int rem_passes = n > 12 ? (n - 12 + 7) / 8 : 0;
     int done_first = 0;
     while (bit_lo < n) {
