@@ -228,6 +228,27 @@ const ml_bfri_proof *ml_bpcs_proof_fri(const ml_bpcs_proof *p);
 size_t ml_bpcs_proof_num_rounds(const ml_bpcs_proof *p);
 int ml_bpcs_proof_sumcheck_coeffs(const ml_bpcs_proof *p, uint8_t *out);
 
+/* ---- sumcheck tables of arbitrary trace width (System path).
+ * Replaces SumcheckTables as built by System::build_tables (src/constraint_system/sumcheck.rs:22-38) with
+ * partial_sum (:204-232), fold (:234-247) and compute_sumcheck_polynomials (:147-202).  The reference passes the
+ * composition as a Rust closure (`&impl Fn(&[F]) -> F`, :176); a closure cannot cross a C ABI, so the caller states the
+ * polynomial it computes over the row:  comp(x) = sum_t coefs[t] * prod_{k < term_lens[t]} x[term_cols[...]]
+ * (term_cols is the concatenation of the terms' column lists; a term of length 0 is the constant coefs[t]).
+ * System::evaluate_composition (evaluation.rs:5-12) = sum_k constraint_mask[k] * expr_k(row) has exactly this form once
+ * the masks and trace challenges are folded into the coefficients.  matrix: the trace, row-major [height][width]. */
+typedef struct ml_wsumcheck ml_wsumcheck;
+int ml_wsumcheck_build(const uint8_t *row_point, size_t n_vars, const uint8_t *matrix, size_t width, size_t height, ml_wsumcheck **out);
+int ml_wsumcheck_build_dev(const uint8_t *row_point, size_t n_vars, const void *matrix_dev, size_t width, size_t height, void *stream, ml_wsumcheck **out);
+void ml_wsumcheck_free(ml_wsumcheck *w);
+size_t ml_wsumcheck_height(const ml_wsumcheck *w);
+size_t ml_wsumcheck_width(const ml_wsumcheck *w);
+int ml_wsumcheck_set_composition(ml_wsumcheck *w, size_t n_terms, const uint8_t *coefs, const uint32_t *term_lens, const uint32_t *term_cols);
+int ml_wsumcheck_tables(const ml_wsumcheck *w, uint8_t *matrix_out, uint8_t *delta_out);
+int ml_wsumcheck_partial_sum(ml_wsumcheck *w, const uint8_t r[16], uint8_t out[16]);                 /* :204-232 */
+int ml_wsumcheck_fold(ml_wsumcheck *w, const uint8_t r[16]);                                         /* :234-247 */
+int ml_wsumcheck_compute_polynomials(ml_wsumcheck *w, size_t composition_degree, ml_transcript *t, const uint8_t sum[16],
+                                     uint8_t *coeffs_out, uint8_t *randoms_out);                     /* :147-202 */
+
 /* ---- batched commit, sharded (BASELINE config 5): one rank's share of `Merkle::batch_commit`
  * (merkle_tree/mod.rs:110-131) over leaf range [leaf_begin, leaf_begin+leaf_count) of all codes.
  * codes_dev[j] points at code j's rows for this range laid out as pairs: leaf_count x 32 bytes.

@@ -548,6 +548,61 @@ class SumcheckTables:
             pass
 
 
+class WideSumcheckTables:
+    """SumcheckTables of arbitrary trace width as built by System::build_tables (src/constraint_system/sumcheck.rs:22-38).
+    The composition closure of the reference (`&impl Fn(&[F]) -> F`) is given as the sparse polynomial it computes over a
+    row: a list of (coefficient, [column, column, ...]) terms."""
+
+    def __init__(self, h, width):
+        self.h, self.width = h, width
+
+    @staticmethod
+    def build(row_point, matrix, width):
+        """matrix: (height*width) elements, row-major; row_point: n_vars elements (ChallengeSet::row)"""
+        rp, m = as_elems(row_point), as_elems(matrix)
+        h = C.c_void_p()
+        check(load().ml_wsumcheck_build(_p(rp), _sz(rp.shape[0]), _p(m), _sz(width), _sz(m.shape[0] // width), C.byref(h)))
+        return WideSumcheckTables(h, width)
+
+    def set_composition(self, terms):
+        coefs = as_elems([c for c, _ in terms]) if terms else elems_empty(1)[:0]
+        lens = np.ascontiguousarray([len(cs) for _, cs in terms], dtype=np.uint32)
+        cols = np.ascontiguousarray([c for _, cs in terms for c in cs] or [0], dtype=np.uint32)
+        check(load().ml_wsumcheck_set_composition(self.h, _sz(len(terms)), _p(coefs), _p(lens), _p(cols)))
+
+    @property
+    def height(self):
+        return load().ml_wsumcheck_height(self.h)
+
+    def tables(self):
+        n = self.height
+        m, d = elems_empty(n * self.width), elems_empty(n)
+        check(load().ml_wsumcheck_tables(self.h, _p(m), _p(d)))
+        return m, d
+
+    def partial_sum(self, r):
+        rb, out = _fe1(r), np.empty(16, dtype=np.uint8)
+        check(load().ml_wsumcheck_partial_sum(self.h, _p(rb), _p(out)))
+        return _int(out)
+
+    def fold(self, r):
+        rb = _fe1(r)
+        check(load().ml_wsumcheck_fold(self.h, _p(rb)))
+
+    def compute_sumcheck_polynomials(self, composition_degree, transcript, s):
+        """-> (flat nonzero coeffs, randoms)  (:147-202)"""
+        n, td = self.height.bit_length() - 1, composition_degree + 1
+        sb, co, rs = _fe1(s), np.empty((max(n, 1) * td, 16), dtype=np.uint8), np.empty((max(n, 1), 16), dtype=np.uint8)
+        check(load().ml_wsumcheck_compute_polynomials(self.h, _sz(composition_degree), transcript.h, _p(sb), _p(co), _p(rs)))
+        return to_ints(co[:n * td]), to_ints(rs[:n])
+
+    def __del__(self):
+        try:
+            load().ml_wsumcheck_free(self.h)
+        except Exception:
+            pass
+
+
 def delta_evaluate(data, points):
     d, p, out = as_elems(data), as_elems(points), np.empty(16, dtype=np.uint8)
     check(load().ml_delta_evaluate(_p(d), _p(p), _sz(d.shape[0]), _p(out)))

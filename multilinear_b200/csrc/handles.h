@@ -60,6 +60,16 @@ struct ml_sumcheck {
     size_t height = 0;
     cudaStream_t stream = nullptr;
 };
+// SumcheckTables with an arbitrary trace width (System path); composition = sparse polynomial over the row
+struct ml_wsumcheck {
+    mlb::fe* matrix = nullptr;  // [height][width] row-major
+    mlb::fe* delta = nullptr;
+    size_t width = 0, height = 0;
+    mlb::fe* coef = nullptr;    // device copies of the composition terms
+    uint32_t *len = nullptr, *off = nullptr, *cols = nullptr;
+    size_t n_terms = 0, n_cols = 0;
+    cudaStream_t stream = nullptr;
+};
 struct ml_pcs_proof {
     ml_fri_proof fri;
     std::vector<mlb::hfe> sumcheck;  // rounds * 2 (c1, c2)

@@ -1263,6 +1263,122 @@ int ml_sumcheck_compute_polynomials(ml_sumcheck* sc, size_t composition_degree, 
     memcpy(&t->sha, host.data() + off_tr, sizeof(DevTranscript));
     return ML_OK;
 }
+// ---- width-w tables (System path): System::build_tables sumcheck.rs:22-38, partial_sum :204-232, fold :234-247,
+// compute_sumcheck_polynomials :147-202 with the composition given as a sparse polynomial over the row
+void free_wsumcheck(ml_wsumcheck* w) {
+    if (!w) return;
+    pfree(w->matrix, w->stream); pfree(w->delta, w->stream); pfree(w->coef, w->stream);
+    pfree(w->len, w->stream); pfree(w->off, w->stream); pfree(w->cols, w->stream);
+    delete w;
+}
+static int wsumcheck_build(Ctx* ctx, const uint8_t* row_point, size_t n_vars, const void* matrix, bool on_device, size_t width, size_t height,
+                           cudaStream_t s, ml_wsumcheck** out) {
+    if (n_vars >= 40 || ((size_t)1 << n_vars) != height) { set_error("trace height must be 2^n_vars"); return ML_ERR_SIZE; }
+    if (width == 0 || width > (size_t)wsumcheck_limits(0)) { set_error("trace width must be 1..%d", wsumcheck_limits(0)); return ML_ERR_ARG; }
+    ml_wsumcheck* w = new ml_wsumcheck();
+    w->width = width; w->height = height; w->stream = s;
+    if (pmalloc((void**)&w->matrix, height * width * 16, s) != ML_OK || pmalloc((void**)&w->delta, height * 16, s) != ML_OK) {
+        free_wsumcheck(w);
+        return ML_ERR_ALLOC;
+    }
+    cudaError_t e = cudaMemcpyAsync(w->matrix, matrix, height * width * 16, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { free_wsumcheck(w); set_error("copy failed: %s", cudaGetErrorString(e)); return ML_ERR_CUDA; }
+    std::vector<hfe> pts(n_vars);
+    for (size_t i = 0; i < n_vars; i++) pts[i] = hfe_load(row_point + 16 * i);
+    int st = eq_table_launch(ctx, pts.data(), n_vars, w->delta, s);  // Mask::evaluate over every index (:26-31)
+    if (st == ML_OK && cudaStreamSynchronize(s) != cudaSuccess) st = ML_ERR_CUDA;
+    if (st != ML_OK) { free_wsumcheck(w); return st; }
+    *out = w;
+    return ML_OK;
+}
+int ml_wsumcheck_build(const uint8_t* row_point, size_t n_vars, const uint8_t* matrix, size_t width, size_t height, ml_wsumcheck** out) {
+    API_BEGIN
+    return wsumcheck_build(ctx, row_point, n_vars, matrix, false, width, height, lib_stream(ctx), out);
+}
+int ml_wsumcheck_build_dev(const uint8_t* row_point, size_t n_vars, const void* matrix_dev, size_t width, size_t height, void* stream,
+                           ml_wsumcheck** out) {
+    API_BEGIN
+    return wsumcheck_build(ctx, row_point, n_vars, matrix_dev, true, width, height, ST(stream), out);
+}
+void ml_wsumcheck_free(ml_wsumcheck* w) { free_wsumcheck(w); }
+size_t ml_wsumcheck_height(const ml_wsumcheck* w) { return w->height; }
+size_t ml_wsumcheck_width(const ml_wsumcheck* w) { return w->width; }
+int ml_wsumcheck_set_composition(ml_wsumcheck* w, size_t n_terms, const uint8_t* coefs, const uint32_t* term_lens, const uint32_t* term_cols) {
+    API_BEGIN
+    (void)ctx;
+    if (n_terms > (size_t)wsumcheck_limits(1)) { set_error("at most %d composition terms", wsumcheck_limits(1)); return ML_ERR_ARG; }
+    std::vector<uint32_t> off(n_terms ? n_terms : 1, 0);
+    size_t total = 0;
+    for (size_t t = 0; t < n_terms; t++) {
+        off[t] = (uint32_t)total;
+        for (uint32_t k = 0; k < term_lens[t]; k++)
+            if (term_cols[total + k] >= w->width) { set_error("composition term %zu references column %u of a width-%zu trace", t, term_cols[total + k], w->width); return ML_ERR_OUT_OF_RANGE; }
+        total += term_lens[t];
+    }
+    if (total > (size_t)wsumcheck_limits(2)) { set_error("at most %d column references", wsumcheck_limits(2)); return ML_ERR_ARG; }
+    cudaStream_t s = w->stream;
+    pfree(w->coef, s); pfree(w->len, s); pfree(w->off, s); pfree(w->cols, s);
+    w->coef = nullptr; w->len = w->off = w->cols = nullptr;
+    MLB_TRY(pmalloc((void**)&w->coef, (n_terms ? n_terms : 1) * 16, s));
+    MLB_TRY(pmalloc((void**)&w->len, (n_terms ? n_terms : 1) * 4, s));
+    MLB_TRY(pmalloc((void**)&w->off, (n_terms ? n_terms : 1) * 4, s));
+    MLB_TRY(pmalloc((void**)&w->cols, (total ? total : 1) * 4, s));
+    MLB_TRY(h2d(w->coef, coefs, n_terms * 16, s));
+    MLB_TRY(h2d(w->len, term_lens, n_terms * 4, s));
+    MLB_TRY(h2d(w->off, off.data(), n_terms * 4, s));
+    MLB_TRY(h2d(w->cols, term_cols, total * 4, s));
+    MLB_CUDA(cudaStreamSynchronize(s));  // off is a host temporary
+    w->n_terms = n_terms; w->n_cols = total;
+    return ML_OK;
+}
+int ml_wsumcheck_tables(const ml_wsumcheck* w, uint8_t* matrix_out, uint8_t* delta_out) {
+    API_BEGIN
+    (void)ctx;
+    MLB_TRY(d2h_sync(matrix_out, w->matrix, w->height * w->width * 16, w->stream));
+    return d2h_sync(delta_out, w->delta, w->height * 16, w->stream);
+}
+static int wpartial(ml_wsumcheck* w, hfe r, hfe* out) {
+    if (w->height < 2) { *out = 0; return ML_OK; }
+    return wsumcheck_partial_sum_launch(w->matrix, w->delta, w->height, w->width, r, w->coef, w->len, w->off, w->cols, w->n_terms, w->n_cols, out, w->stream);
+}
+int ml_wsumcheck_partial_sum(ml_wsumcheck* w, const uint8_t r[16], uint8_t out[16]) {
+    API_BEGIN
+    (void)ctx;
+    hfe o;
+    MLB_TRY(wpartial(w, hfe_load(r), &o));
+    hfe_store(out, o);
+    return ML_OK;
+}
+int ml_wsumcheck_fold(ml_wsumcheck* w, const uint8_t r[16]) {
+    API_BEGIN
+    (void)ctx;
+    MLB_TRY(wsumcheck_fold_launch(w->matrix, w->delta, w->height, w->width, hfe_load(r), w->stream));
+    w->height >>= 1;
+    return ML_OK;
+}
+int ml_wsumcheck_compute_polynomials(ml_wsumcheck* w, size_t composition_degree, ml_transcript* t, const uint8_t sum[16], uint8_t* coeffs_out,
+                                     uint8_t* randoms_out) {
+    API_BEGIN
+    (void)ctx;
+    const size_t td = composition_degree + 1;  // :159
+    if (td > 16) { set_error("composition_degree too large"); return ML_ERR_ARG; }
+    const size_t rounds = w->height ? ilog2(w->height) : 0;
+    hfe prev = hfe_load(sum);
+    std::vector<hfe> evals(td + 1), coeffs;
+    for (size_t k = 0; k < rounds; k++) {
+        for (size_t i = 1; i <= td; i++) MLB_TRY(wpartial(w, hfe_new((hfe)i), &evals[i]));  // :185-187
+        evals[0] = hfe_sub(prev, evals[1]);                                                 // :188
+        interpolate(evals, coeffs);                                                         // :189-192
+        for (size_t i = 1; i <= td; i++) { hfe_store(coeffs_out + 16 * (k * td + i - 1), coeffs[i]); absorb_fe(t, coeffs[i]); }
+        hfe r = challenge(t);                                                               // :198
+        prev = poly_eval(coeffs, r);                                                        // :199
+        MLB_TRY(wsumcheck_fold_launch(w->matrix, w->delta, w->height, w->width, r, w->stream));  // :200
+        w->height >>= 1;
+        hfe_store(randoms_out + 16 * k, r);
+    }
+    MLB_CUDA(cudaStreamSynchronize(w->stream));
+    return ML_OK;
+}
 int ml_delta_evaluate(const uint8_t* data, const uint8_t* points, size_t n, uint8_t out[16]) {
     std::vector<hfe> a(n), b(n);
     for (size_t i = 0; i < n; i++) { a[i] = hfe_load(data + 16 * i); b[i] = hfe_load(points + 16 * i); }

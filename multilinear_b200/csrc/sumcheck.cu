@@ -112,6 +112,68 @@ __global__ void __launch_bounds__(SC_THREADS) sumcheck_fold_sums_kernel(fe* __re
     }
 }
 
+// ---------------------------------------------------------------- width-w tables (System path, sumcheck.rs:21-38, 204-247)
+// matrix is the trace, row-major [height][width]; the composition is a sparse polynomial over the row
+//     comp(x) = sum_t coef[t] * prod_{k < len[t]} x[cols[off[t] + k]]
+// (the C-ABI stand-in for the reference's closure argument, sumcheck.rs:176).  Terms live in shared memory; a thread
+// interpolates one row pair, evaluates the composition and accumulates comp * delta unreduced.
+struct WTerms {
+    const fe* coef;
+    const uint32_t* len;
+    const uint32_t* off;
+    const uint32_t* cols;
+    int n_terms, n_cols;
+};
+static const int W_MAX_WIDTH = 16, W_MAX_TERMS = 64, W_MAX_COLS = 256;
+__global__ void __launch_bounds__(SC_THREADS) wsumcheck_partial_kernel(const fe* __restrict__ m, const fe* __restrict__ d, size_t off, int width,
+                                                                       fe r, fe sm1, int is_one, WTerms terms, fe* __restrict__ partials) {
+    __shared__ fe scratch[32];
+    __shared__ fe t_coef[W_MAX_TERMS];
+    __shared__ uint32_t t_len[W_MAX_TERMS], t_off[W_MAX_TERMS], t_cols[W_MAX_COLS];
+    for (int t = threadIdx.x; t < terms.n_terms; t += blockDim.x) { t_coef[t] = terms.coef[t]; t_len[t] = terms.len[t]; t_off[t] = terms.off[t]; }
+    for (int c = threadIdx.x; c < terms.n_cols; c += blockDim.x) t_cols[c] = terms.cols[c];
+    __syncthreads();
+    fe_acc a;
+    acc_zero(a);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < off; i += stride) {
+        fe row[W_MAX_WIDTH];
+        fe dd;
+        if (is_one) {  // :208-218 (r * x with r = 1)
+            dd = fe_load_nc(d + i + off);
+            for (int j = 0; j < width; j++) row[j] = fe_load_nc(m + (i + off) * width + j);
+        } else {       // :219-231
+            dd = fe_add(fe_mul(sm1, fe_load_nc(d + i)), fe_mul(r, fe_load_nc(d + i + off)));
+            for (int j = 0; j < width; j++)
+                row[j] = fe_add(fe_mul(sm1, fe_load_nc(m + i * width + j)), fe_mul(r, fe_load_nc(m + (i + off) * width + j)));
+        }
+        fe comp = fe_zero();
+        for (int t = 0; t < terms.n_terms; t++) {
+            fe p = t_coef[t];
+            for (uint32_t k = 0; k < t_len[t]; k++) p = fe_mul(p, row[t_cols[t_off[t] + k]]);
+            comp = fe_add(comp, p);
+        }
+        acc_mul_add(a, comp, dd);
+    }
+    fe s = block_sum(acc_reduce(a), scratch);
+    if (threadIdx.x == 0) fe_store(partials + blockIdx.x, s);
+}
+// fold (:234-247): rows i < off of the matrix and of delta, x <- x + r (x[i+off] - x)
+__global__ void __launch_bounds__(256) wsumcheck_fold_kernel(fe* __restrict__ m, fe* __restrict__ d, size_t off, int width, fe r) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t total = off * (size_t)(width + 1);
+    for (; e < total; e += stride) {
+        fe* base;
+        size_t idx, hi;
+        if (e < off * (size_t)width) { base = m; idx = e; hi = e + off * (size_t)width; }
+        else { base = d; idx = e - off * (size_t)width; hi = idx + off; }
+        fe x0 = fe_load(base + idx), x1 = fe_load(base + hi);
+        fe_store(base + idx, fe_add(x0, fe_mul(r, fe_sub(x1, x0))));
+    }
+}
+
 static inline unsigned blocks_for(size_t n) {
     size_t b = (n + SC_THREADS - 1) / SC_THREADS;
     if (b > (size_t)SC_MAX_BLOCKS) b = SC_MAX_BLOCKS;
@@ -188,4 +250,32 @@ int sumcheck_fold_launch(fe* m, fe* d, size_t height, hfe r, const fe* r_dev, cu
     return ML_OK;
 }
 
+}  // namespace mlb
+
+namespace mlb {
+int wsumcheck_limits(int what) { return what == 0 ? W_MAX_WIDTH : what == 1 ? W_MAX_TERMS : W_MAX_COLS; }
+int wsumcheck_partial_sum_launch(const fe* m, const fe* d, size_t height, size_t width, hfe r, const fe* coef, const uint32_t* len,
+                                 const uint32_t* off, const uint32_t* cols, size_t n_terms, size_t n_cols, hfe* out, cudaStream_t s) {
+    const size_t half = height >> 1;
+    const unsigned nb = blocks_for(half);
+    fe* partials;
+    MLB_TRY(dev_alloc_async((void**)&partials, (size_t)(nb + 1) * 16, s));
+    WTerms t{coef, len, off, cols, (int)n_terms, (int)n_cols};
+    wsumcheck_partial_kernel<<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, to_dev_fe_h(r), to_dev_fe_h(hfe_sub(1, r)), r == 1 ? 1 : 0, t, partials);
+    MLB_KERNEL_CHECK();
+    reduce_partials_kernel<<<1, 256, 0, s>>>(partials, (int)nb, 1, partials + nb);
+    MLB_KERNEL_CHECK();
+    MLB_TRY(fetch(partials + nb, 1, out, s));
+    MLB_TRY(dev_free_async(partials, s));
+    return ML_OK;
+}
+int wsumcheck_fold_launch(fe* m, fe* d, size_t height, size_t width, hfe r, cudaStream_t s) {
+    const size_t half = height >> 1;
+    if (half == 0) return ML_OK;
+    size_t total = half * (width + 1), blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wsumcheck_fold_kernel<<<(unsigned)blocks, 256, 0, s>>>(m, d, half, (int)width, to_dev_fe_h(r));
+    MLB_KERNEL_CHECK();
+    return ML_OK;
+}
 }  // namespace mlb

@@ -32,12 +32,12 @@ def lib():
         L = C.CDLL(so)
         vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
         ptr_fns = ["or_transcript_new", "or_transcript_clone", "or_merkle_commit", "or_merkle_batch_commit", "or_fri_init",
-                   "or_fri_fold", "or_fri_tree", "or_fri_prove", "or_sumcheck_build_tables_for_pcs", "or_pcs_prove",
+                   "or_fri_fold", "or_fri_tree", "or_fri_prove", "or_sumcheck_build_tables_for_pcs", "or_wsumcheck_build", "or_pcs_prove",
                    "or_pcs_proof_fri", "or_batched_fri_prove", "or_batched_pcs_prove", "or_bpcs_proof_fri"]
         for f in ptr_fns:
             getattr(L, f).restype = vp
         for f in ["or_merkle_num_layers", "or_merkle_layer_len", "or_fri_num_trees", "or_fri_proof_serialized_len",
-                  "or_fri_proof_num_commitments", "or_sumcheck_height", "or_pcs_proof_num_rounds",
+                  "or_fri_proof_num_commitments", "or_sumcheck_height", "or_wsumcheck_height", "or_pcs_proof_num_rounds",
                   "or_bfri_proof_serialized_len", "or_bfri_proof_num_commitments", "or_bpcs_proof_num_rounds"]:
             getattr(L, f).restype = sz
         # every pointer/size argument is passed explicitly typed by the helpers below
@@ -342,6 +342,57 @@ class OrFri:
             pass
 
 
+
+def composition_arrays(terms):
+    """[(coef int, [cols...]), ...] -> (coefs (n,16) u8, lens u32, cols u32): the sparse-polynomial form of a composition"""
+    coefs = fe_arr([c for c, _ in terms]) if terms else np.empty((0, 16), dtype=np.uint8)
+    lens = np.array([len(cs) for _, cs in terms], dtype=np.uint32)
+    cols = np.array([c for _, cs in terms for c in cs] or [0], dtype=np.uint32)
+    return np.ascontiguousarray(coefs), np.ascontiguousarray(lens), np.ascontiguousarray(cols)
+
+
+class OrWSumcheck:
+    """width-w SumcheckTables (System path), composition = sparse polynomial over the row"""
+
+    def __init__(self, L, h, width):
+        self.L, self.h, self.width = L, C.c_void_p(h), width
+
+    def height(self):
+        return self.L.or_wsumcheck_height(self.h)
+
+    def set_composition(self, terms):
+        coefs, lens, cols = composition_arrays(terms)
+        assert self.L.or_wsumcheck_set_composition(self.h, sz(len(terms)), buf(coefs), buf(lens), buf(cols)) == 0
+
+    def tables(self):
+        n = self.height()
+        m, d = elems_empty(n * self.width), elems_empty(n)
+        self.L.or_wsumcheck_tables(self.h, buf(m), buf(d))
+        return m, d
+
+    def partial_sum(self, r):
+        out, rb = np.empty(16, dtype=np.uint8), fe1(r)
+        self.L.or_wsumcheck_partial_sum(self.h, buf(rb), buf(out))
+        return fe_int(out)
+
+    def fold(self, r):
+        rb = fe1(r)
+        self.L.or_wsumcheck_fold(self.h, buf(rb))
+
+    def compute_sumcheck_polynomials(self, composition_degree, t, s):
+        n = (self.height()).bit_length() - 1
+        td = composition_degree + 1
+        sb, co, rs = fe1(s), np.empty((max(n, 1) * td, 16), dtype=np.uint8), np.empty((max(n, 1), 16), dtype=np.uint8)
+        self.L.or_wsumcheck_compute_polynomials(self.h, sz(composition_degree), t.h, buf(sb), buf(co), buf(rs))
+        return fe_ints(co[:n * td]), fe_ints(rs[:n])
+
+    def __del__(self):
+        try:
+            self.L.or_wsumcheck_free(self.h)
+        except Exception:
+            pass
+
+
 class OrSumcheck:
     def __init__(self, L, h):
         self.L, self.h = L, C.c_void_p(h)
@@ -428,6 +479,23 @@ def _ext(cls):
         h = self.L.or_sumcheck_build_tables_for_pcs(buf(inputs), sz(inputs.shape[0]), buf(evals), sz(evals.shape[0]))
         return OrSumcheck(self.L, h) if h else None
 
+    def wsumcheck_build(self, row_point, matrix, width):
+        """matrix: (height*width, 16) row-major trace; row_point: (n_vars, 16)"""
+        height = matrix.shape[0] // width
+        h = self.L.or_wsumcheck_build(buf(row_point), sz(row_point.shape[0]), buf(matrix), sz(width), sz(height))
+        return OrWSumcheck(self.L, h, width) if h else None
+
+    def trace_evaluate(self, matrix, width, points):
+        height = matrix.shape[0] // width
+        out = np.empty((width, 16), dtype=np.uint8)
+        self.L.or_trace_evaluate(buf(matrix), sz(width), sz(height), buf(points), buf(out))
+        return fe_ints(out)
+
+    def mask_evaluate(self, index, points):
+        out = np.empty(16, dtype=np.uint8)
+        self.L.or_mask_evaluate(sz(index), sz(points.shape[0]), buf(points), buf(out))
+        return fe_int(out)
+
     def delta_evaluate(self, data, points):
         out = np.empty(16, dtype=np.uint8)
         self.L.or_delta_evaluate(buf(data), buf(points), sz(data.shape[0]), buf(out))
@@ -459,7 +527,7 @@ def _ext(cls):
                                         sz(polys[0].shape[0]), t.h, C.byref(st))
         return (OrPcsProof(self.L, h, batched=True) if h else None), st.value
 
-    for f in (fri_init, fri_fold, fri_prove, sumcheck_build, delta_evaluate, pcs_prove, fingerprint, batched_fri_prove,
+    for f in (fri_init, fri_fold, fri_prove, sumcheck_build, wsumcheck_build, trace_evaluate, mask_evaluate, delta_evaluate, pcs_prove, fingerprint, batched_fri_prove,
               batched_pcs_prove):
         setattr(cls, f.__name__, f)
 

@@ -779,6 +779,132 @@ void or_sumcheck_compute_polynomials(or_sumcheck *s, size_t composition_degree, 
         fe_store(randoms_out + 16 * k, r);
     }
 }
+/* ---------------------------------------------------------- width-w sumcheck tables (System path)
+ * SumcheckTables with an arbitrary trace width (src/constraint_system/sumcheck.rs:10-15, System::build_tables :22-38,
+ * partial_sum :204-232, fold :234-247, compute_sumcheck_polynomial(s) :147-202).  The reference passes the composition as a
+ * Rust closure (`&impl Fn(&[F]) -> F`, :176; System::evaluate_composition, evaluation.rs:5-12 = sum_k mask_k * expr_k(row)).
+ * A closure cannot cross a C ABI, so a composition is given as the sparse polynomial it computes over the row:
+ *     comp(x) = sum_t coef[t] * prod_{k < len[t]} x[cols[off[t] + k]]       (len[t] = 0: the constant coef[t]) */
+struct or_wsumcheck {
+    fe *matrix, *delta;
+    size_t width, height;
+    size_t n_terms;
+    fe *coef;
+    uint32_t *len, *off, *cols;
+};
+or_wsumcheck *or_wsumcheck_build(const uint8_t *row_point, size_t n_vars, const uint8_t *matrix, size_t width, size_t height) {
+    if (n_vars >= 64 || ((size_t)1 << n_vars) != height || width == 0) return NULL;
+    or_wsumcheck *s = (or_wsumcheck *)calloc(1, sizeof *s);
+    s->width = width; s->height = height;
+    s->matrix = (fe *)malloc(height * width * sizeof(fe));
+    s->delta = (fe *)malloc(height * sizeof(fe));
+    memcpy(s->matrix, matrix, height * width * 16);                                          /* :33 */
+    const fe *pts = (const fe *)row_point;
+    PAR_FOR for (size_t idx = 0; idx < height; idx++) s->delta[idx] = mask_evaluate(idx, n_vars, pts); /* :26-31 */
+    return s;
+}
+void or_wsumcheck_free(or_wsumcheck *s) {
+    if (s) { free(s->matrix); free(s->delta); free(s->coef); free(s->len); free(s->off); free(s->cols); free(s); }
+}
+size_t or_wsumcheck_height(const or_wsumcheck *s) { return s->height; }
+void or_wsumcheck_tables(const or_wsumcheck *s, uint8_t *m, uint8_t *d) {
+    memcpy(m, s->matrix, s->height * s->width * 16);
+    memcpy(d, s->delta, s->height * 16);
+}
+int or_wsumcheck_set_composition(or_wsumcheck *s, size_t n_terms, const uint8_t *coefs, const uint32_t *term_lens, const uint32_t *term_cols) {
+    size_t total = 0;
+    for (size_t t = 0; t < n_terms; t++) {
+        for (uint32_t k = 0; k < term_lens[t]; k++) if (term_cols[total + k] >= s->width) return 1;
+        total += term_lens[t];
+    }
+    free(s->coef); free(s->len); free(s->off); free(s->cols);
+    s->n_terms = n_terms;
+    s->coef = (fe *)malloc((n_terms ? n_terms : 1) * sizeof(fe));
+    s->len = (uint32_t *)malloc((n_terms ? n_terms : 1) * sizeof(uint32_t));
+    s->off = (uint32_t *)malloc((n_terms ? n_terms : 1) * sizeof(uint32_t));
+    s->cols = (uint32_t *)malloc((total ? total : 1) * sizeof(uint32_t));
+    memcpy(s->coef, coefs, n_terms * 16);
+    memcpy(s->len, term_lens, n_terms * sizeof(uint32_t));
+    memcpy(s->cols, term_cols, total * sizeof(uint32_t));
+    uint32_t o = 0;
+    for (size_t t = 0; t < n_terms; t++) { s->off[t] = o; o += term_lens[t]; }
+    return 0;
+}
+static fe wcomposition(const or_wsumcheck *s, const fe *row) {
+    fe acc = 0;
+    for (size_t t = 0; t < s->n_terms; t++) {
+        fe p = s->coef[t];
+        for (uint32_t k = 0; k < s->len[t]; k++) p = fe_mul(p, row[s->cols[s->off[t] + k]]);
+        acc = fe_add(acc, p);
+    }
+    return acc;
+}
+static fe wpartial_sum(const or_wsumcheck *s, fe r) { /* :204-232 */
+    size_t offset = s->height >> 1, w = s->width;
+    fe one = fe_from_i64(1), sm1 = fe_sub(one, r), acc = 0;
+    int is_one = (r == one);
+    fe *row = (fe *)malloc(w * sizeof(fe));
+    for (size_t i = 0; i < offset; i++) {
+        fe d;
+        if (is_one) {
+            d = fe_mul(r, s->delta[i + offset]);
+            for (size_t j = 0; j < w; j++) row[j] = fe_mul(r, s->matrix[(i + offset) * w + j]);
+        } else {
+            d = fe_add(fe_mul(sm1, s->delta[i]), fe_mul(r, s->delta[i + offset]));
+            for (size_t j = 0; j < w; j++) row[j] = fe_add(fe_mul(sm1, s->matrix[i * w + j]), fe_mul(r, s->matrix[(i + offset) * w + j]));
+        }
+        acc = fe_add(acc, fe_mul(wcomposition(s, row), d));
+    }
+    free(row);
+    return acc;
+}
+void or_wsumcheck_partial_sum(const or_wsumcheck *s, const uint8_t r[16], uint8_t out[16]) { fe_store(out, wpartial_sum(s, fe_load(r))); }
+static void wfold(or_wsumcheck *s, fe r) { /* :234-247 */
+    s->height >>= 1;
+    size_t offset = s->height, w = s->width;
+    fe sm1 = fe_sub(fe_from_i64(1), r);
+    for (size_t i = 0; i < offset; i++) {
+        s->delta[i] = fe_add(fe_mul(sm1, s->delta[i]), fe_mul(r, s->delta[i + offset]));
+        for (size_t j = 0; j < w; j++)
+            s->matrix[i * w + j] = fe_add(fe_mul(sm1, s->matrix[i * w + j]), fe_mul(r, s->matrix[(i + offset) * w + j]));
+    }
+}
+void or_wsumcheck_fold(or_wsumcheck *s, const uint8_t r[16]) { wfold(s, fe_load(r)); }
+void or_wsumcheck_compute_polynomials(or_wsumcheck *s, size_t composition_degree, or_transcript *t, const uint8_t sum[16],
+                                      uint8_t *coeffs_out, uint8_t *randoms_out) { /* :147-202 */
+    fe prev = fe_load(sum);
+    size_t total_degree = composition_degree + 1, np = total_degree + 1, n_rounds = ctz_sz(s->height);
+    fe *evals = (fe *)calloc(np, sizeof(fe)), *coeffs = (fe *)calloc(np, sizeof(fe));
+    for (size_t k = 0; k < n_rounds; k++) {
+        for (size_t i = 1; i < np; i++) evals[i] = wpartial_sum(s, fe_from_i64((int64_t)i));
+        evals[0] = fe_sub(prev, evals[1]);
+        interpolate(evals, np, coeffs);
+        for (size_t i = 1; i < np; i++) { fe_store(coeffs_out + 16 * (k * total_degree + i - 1), coeffs[i]); absorb_fe(t, coeffs[i]); }
+        fe r = transcript_challenge(t);
+        prev = poly_eval(coeffs, np, r);
+        wfold(s, r);
+        fe_store(randoms_out + 16 * k, r);
+    }
+    free(evals); free(coeffs);
+}
+/* Trace::evaluate (evaluation.rs:33-48): res[j] = sum_index Mask(index)(points) * matrix[index][j] */
+void or_trace_evaluate(const uint8_t *matrix, size_t width, size_t height, const uint8_t *points, uint8_t *out) {
+    size_t n_vars = ctz_sz(height);
+    const fe *m = (const fe *)matrix, *pts = (const fe *)points;
+    for (size_t j = 0; j < width; j++) fe_store(out + 16 * j, 0);
+    fe *res = (fe *)calloc(width, sizeof(fe));
+    for (size_t index = 0; index < height; index++) {
+        fe c = mask_evaluate(index, n_vars, pts);
+        for (size_t j = 0; j < width; j++) res[j] = fe_add(res[j], fe_mul(c, m[index * width + j]));
+    }
+    for (size_t j = 0; j < width; j++) fe_store(out + 16 * j, res[j]);
+    free(res);
+}
+/* Mask::evaluate for one index (evaluation.rs:56-73): used for System's constraint_mask (system.rs:91-93) */
+void or_mask_evaluate(size_t index, size_t n_vars, const uint8_t *points, uint8_t out[16]) {
+    fe_store(out, mask_evaluate(index, n_vars, (const fe *)points));
+}
+
 /* Delta::evaluate, src/constraint_system/evaluation.rs:80-90 */
 static fe delta_evaluate(const fe *data, const fe *points, size_t n) {
     fe one = fe_from_i64(1), prod = fe_from_i64(1);

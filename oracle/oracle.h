@@ -121,6 +121,21 @@ void or_sumcheck_compute_polynomials(or_sumcheck *s, size_t composition_degree, 
                                      uint8_t *coeffs_out, uint8_t *randoms_out);          /* :147-172 */
 void or_delta_evaluate(const uint8_t *data, const uint8_t *points, size_t n, uint8_t out[16]); /* evaluation.rs:80-90 */
 
+/* ---- width-w sumcheck tables (System path, src/constraint_system/sumcheck.rs:21-38, 147-247); the composition closure is
+ * restated as a sparse polynomial over the row: sum_t coef[t] * prod_k x[cols[..]] ---- */
+typedef struct or_wsumcheck or_wsumcheck;
+or_wsumcheck *or_wsumcheck_build(const uint8_t *row_point, size_t n_vars, const uint8_t *matrix, size_t width, size_t height); /* :22-38 */
+void or_wsumcheck_free(or_wsumcheck *s);
+size_t or_wsumcheck_height(const or_wsumcheck *s);
+void or_wsumcheck_tables(const or_wsumcheck *s, uint8_t *matrix_out, uint8_t *delta_out);
+int or_wsumcheck_set_composition(or_wsumcheck *s, size_t n_terms, const uint8_t *coefs, const uint32_t *term_lens, const uint32_t *term_cols);
+void or_wsumcheck_partial_sum(const or_wsumcheck *s, const uint8_t r[16], uint8_t out[16]);   /* :204-232 */
+void or_wsumcheck_fold(or_wsumcheck *s, const uint8_t r[16]);                                 /* :234-247 */
+void or_wsumcheck_compute_polynomials(or_wsumcheck *s, size_t composition_degree, or_transcript *t, const uint8_t sum[16],
+                                      uint8_t *coeffs_out, uint8_t *randoms_out);             /* :147-202 */
+void or_trace_evaluate(const uint8_t *matrix, size_t width, size_t height, const uint8_t *points, uint8_t *out); /* evaluation.rs:33-48 */
+void or_mask_evaluate(size_t index, size_t n_vars, const uint8_t *points, uint8_t out[16]);   /* evaluation.rs:56-73 */
+
 /* ---- multilinear PCS (src/fri/multilinear_pcs.rs) ---- */
 typedef struct or_pcs_proof or_pcs_proof;
 or_pcs_proof *or_pcs_prove(const uint8_t *inputs, size_t n_vars, const uint8_t output[16], const uint8_t *evals, size_t n,

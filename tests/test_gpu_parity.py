@@ -364,6 +364,55 @@ def test_batched_pcs_vs_oracle(ml, oracle, nv, B):
     assert t.random() == ot.random() and proof.verify(ml.Transcript()) == 0
 
 
+# ------------------------------------------------------------------ width-w sumcheck tables (System path)
+@pytest.mark.parametrize("log_height", [4, 7, 13])
+def test_wide_sumcheck_reference_sumcheck_test(ml, oracle, log_height):
+    """the reference's sumcheck_test / sumcheck_high_bench (sumcheck.rs:342-398): pythagorean trace (width 4), two
+    constraints under the constraint mask, sum 0; bit-exact against the oracle, and accepted by verify_sumcheck_debug"""
+    from test_oracle import pythagorean_system, verify_sumcheck_debug
+    matrix, row_point, terms, ot = pythagorean_system(oracle, log_height)
+    o = oracle.wsumcheck_build(row_point, matrix, 4)
+    o.set_composition(terms)
+    g = ml.WideSumcheckTables.build(row_point, matrix, 4)
+    g.set_composition(terms)
+    gm, gd = g.tables()
+    om, od = o.tables()
+    assert np.array_equal(gm, om) and np.array_equal(gd, od)
+    for r in (1, 2, 3, 0, M - 1, 123456789):
+        assert g.partial_sum(r) == o.partial_sum(r)
+    t = ml.Transcript()
+    gp, grs = g.compute_sumcheck_polynomials(2, t, 0)
+    op, ors = o.compute_sumcheck_polynomials(2, ot, 0)
+    assert gp == op and grs == ors and g.height == 1
+    assert t.random() == ot.random()
+    assert verify_sumcheck_debug(oracle, oracle.transcript(), gp, 3, 0, matrix, 4, row_point, terms) == grs
+
+
+def test_wide_sumcheck_fold_random_and_errors(ml, oracle):
+    from multilinear_b200._lib import MlError
+    nv, w = 9, 5
+    matrix = oracle.synthetic(31, w << nv)
+    row_point = oracle.synthetic(32, nv)
+    terms = [(7, [0, 1, 2]), (M - 3, [4, 4]), (11, []), (5, [3])]  # degree 3, with a constant term
+    o = oracle.wsumcheck_build(row_point, matrix, w)
+    g = ml.WideSumcheckTables.build(row_point, matrix, w)
+    o.set_composition(terms)
+    g.set_composition(terms)
+    for r in (5, M - 2, 1 << 100):
+        assert g.partial_sum(r) == o.partial_sum(r)
+        g.fold(r)
+        o.fold(r)
+        gm, gd = g.tables()
+        om, od = o.tables()
+        assert np.array_equal(gm, om) and np.array_equal(gd, od)
+    t, ot = ml.Transcript(), oracle.transcript()
+    assert g.compute_sumcheck_polynomials(3, t, 99) == o.compute_sumcheck_polynomials(3, ot, 99)
+    with pytest.raises(MlError):
+        g.set_composition([(1, [w])])  # column out of range
+    with pytest.raises(MlError):
+        ml.WideSumcheckTables.build(row_point, matrix[:w * 100], w)  # height not 2^n_vars
+
+
 # ------------------------------------------------------------------ sharded batched commit (config 5), single GPU
 @pytest.mark.parametrize("mode", ["serial", "pipelined", "p2p"])
 def test_sharded_batch_commit_single_gpu(ml, oracle, mode):
@@ -422,6 +471,36 @@ def test_fullsize_commit_prove_verify_2p22(ml):
     out = ml.MultilinearPolynomialEvals(evals).evaluate(ml.to_ints(inp))
     p = ml.PCSProof.prove(inp, out, evals, ml.Transcript())
     assert p.verify(ml.Transcript()) == 0
+
+
+def test_maxsize_ntt_roundtrip_2p27_device_resident(ml):
+    """largest transform that a 4-level pass plan is exercised on here: 2^27 elements (2 GiB per array), device resident.
+    intt(ntt(x)) == x and intt(reed_solomon(c)) == c || 0, compared through Merkle roots (a checksum of checksums) so
+    nothing but 32 bytes crosses PCIe."""
+    import ctypes as C
+    from multilinear_b200 import load
+    L = load()
+    log_n = 27
+    n = 1 << log_n
+    g = ml.pow_2_generator(log_n)
+    gb = (C.c_uint8 * 16)(*g.to_bytes(16, "little"))
+    x = ml.synthetic_elements_dev(21, n)
+    y = ml.DeviceBuffer(16 * n)
+    z = ml.DeviceBuffer(16 * n)
+    ml.check(L.ml_ntt_dev(x.ptr, C.c_size_t(n), gb, y.ptr, None))
+    ml.check(L.ml_intt_dev(y.ptr, C.c_size_t(n), gb, z.ptr, None))
+    rx = ml.Merkle.commit_rs_code_dev(x, n).root()
+    assert ml.Merkle.commit_rs_code_dev(z, n).root() == rx
+    assert ml.Merkle.commit_rs_code_dev(y, n).root() != rx
+    # RS encode of the first half (2^26 coefficients -> 2^27 evaluations), inverted, gives the coefficients and a zero half
+    ml.check(L.ml_reed_solomon_dev(x.ptr, C.c_size_t(n // 2), gb, y.ptr, None))
+    ml.check(L.ml_intt_dev(y.ptr, C.c_size_t(n), gb, z.ptr, None))
+    head = z.to_host(16 * 4096).reshape(-1, 16)
+    assert np.array_equal(head, x.to_host(16 * 4096).reshape(-1, 16))
+    ml.check(L.ml_dev_download(C.c_void_p(head.ctypes.data), C.c_void_p(z.ptr.value + 16 * (n - 4096)), C.c_size_t(16 * 4096)))
+    assert not head.any()
+    for b in (x, y, z):
+        b.free()
 
 
 # ------------------------------------------------------------------ the reference's own tests on the C++ host mirror

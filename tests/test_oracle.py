@@ -4,6 +4,7 @@ import os
 import random
 
 import numpy as np
+import pytest
 
 from oracle import pyref as P
 from oracle.binding import fe_arr, fe_ints
@@ -206,3 +207,92 @@ def test_synthetic_generator(oracle):
     a = oracle.synthetic(0xB200, 1000)
     assert np.array_equal(a, oracle.synthetic(0xB200, 1000)) and all(x < M for x in fe_ints(a))
     assert not np.array_equal(a, oracle.synthetic(0xB201, 1000))
+
+
+# ------------------------------------------------------------------ width-w sumcheck tables (System path)
+PYTHAGOREAN = [3, 4, 5, 7, 5, 12, 13, 17, 8, 15, 17, 23, 7, 24, 25, 31, 20, 21, 29, 41, 12, 35, 37, 47, 9, 40, 41, 49, 28, 45, 53, 73,
+               11, 60, 61, 71, 16, 63, 65, 79, 33, 56, 65, 89, 48, 55, 73, 103, 13, 84, 85, 97, 36, 77, 85, 113, 39, 80, 89, 119,
+               65, 72, 97, 137]  # src/constraint_system/sumcheck.rs:302-325
+
+
+def pythagorean_terms(m0, m1):
+    """System::evaluate_composition for pythagorean_set (:333-339): mask0 * (x0^2 + x1^2 - x2^2) + mask1 * (x0 + x1 - x3)"""
+    return [(m0, [0, 0]), (m0, [1, 1]), ((-m0) % M, [2, 2]), (m1, [0]), (m1, [1]), ((-m1) % M, [3])]
+
+
+def eval_terms(terms, x):
+    acc = 0
+    for c, cols in terms:
+        for j in cols:
+            c = c * x[j] % M
+        acc = (acc + c) % M
+    return acc
+
+
+def verify_sumcheck_debug(oracle, t, pols, total_degree, s, matrix, width, row_point, terms):
+    """System::verify_sumcheck_debug (sumcheck.rs:55-90) restated on the oracle's primitives"""
+    def to_poly(nz, sm):  # SumcheckPolynomial::to_polynomial (:269-276)
+        return [(sm - sum(nz)) * pow(2, -1, M) % M] + list(nz)
+
+    def ev(p, x):
+        a = 0
+        for c in reversed(p):
+            a = (a * x + c) % M
+        return a
+    rounds = [pols[total_degree * k:total_degree * (k + 1)] for k in range(len(pols) // total_degree)]
+    for c in rounds[0]:
+        t.absorb(int(c).to_bytes(16, "little"))
+    pol, rs = to_poly(rounds[0], s), []
+    for p in rounds[1:]:
+        r = t.next_challenge()
+        for c in p:
+            t.absorb(int(c).to_bytes(16, "little"))
+        pol = to_poly(p, ev(pol, r))
+        rs.append(r)
+    r = t.next_challenge()
+    rs.append(r)
+    out = oracle.trace_evaluate(matrix, width, fe_arr(rs))
+    delta = oracle.delta_evaluate(row_point, fe_arr(rs))
+    assert delta * eval_terms(terms, out) % M == ev(pol, r), "Does not match polynomial evaluation"
+    return rs
+
+
+def pythagorean_system(oracle, log_height=4):
+    """the reference's sumcheck_test / sumcheck_high_bench set-up (:342-398): trace, ChallengeSet, constraint mask"""
+    rows = list(PYTHAGOREAN)
+    while len(rows) < 4 << log_height:
+        rows = rows + rows
+    matrix = fe_arr(rows)
+    t = oracle.transcript()
+    c = t.next_challenge()  # ChallengeSet::new (system.rs:132-147): the transcript is not mutated, every challenge is c
+    row_point, cons = fe_arr([c] * log_height), fe_arr([c])
+    m0, m1 = oracle.mask_evaluate(0, cons), oracle.mask_evaluate(1, cons)  # system.rs:91-93
+    assert m0 == (1 - c) % M and m1 == c
+    return matrix, row_point, pythagorean_terms(m0, m1), t
+
+
+@pytest.mark.parametrize("log_height", [4, 7])
+def test_wide_sumcheck_reference_sumcheck_test(oracle, log_height):
+    matrix, row_point, terms, t = pythagorean_system(oracle, log_height)
+    s = oracle.wsumcheck_build(row_point, matrix, 4)
+    s.set_composition(terms)
+    m, d = s.tables()
+    assert np.array_equal(m, matrix)
+    assert fe_ints(d)[5] == oracle.mask_evaluate(5, row_point)
+    vt = oracle.transcript()
+    pols, rs = s.compute_sumcheck_polynomials(2, t, 0)  # constraints.degree() = 2 (:338), sum = 0 (:350)
+    assert len(pols) == 3 * log_height and s.height() == 1
+    assert verify_sumcheck_debug(oracle, vt, pols, 3, 0, matrix, 4, row_point, terms) == rs
+
+
+def test_wide_sumcheck_width1_equals_pcs_tables(oracle):
+    """width 1 with the composition x[0] is exactly the PCS specialisation (multilinear_pcs.rs:56-57)"""
+    nv = 6
+    evals = oracle.synthetic(77, 1 << nv)
+    inputs = fe_arr([3 * i + 2 for i in range(nv)])
+    claim = oracle.mle_evals_evaluate(evals, inputs)
+    a = oracle.sumcheck_build(inputs, evals)
+    b = oracle.wsumcheck_build(inputs, evals, 1)
+    b.set_composition([(1, [0])])
+    assert a.partial_sum(2) == b.partial_sum(2) and a.partial_sum(1) == b.partial_sum(1)
+    assert a.compute_sumcheck_polynomials(1, oracle.transcript(), claim) == b.compute_sumcheck_polynomials(1, oracle.transcript(), claim)
