@@ -12,6 +12,7 @@ use crate::fri::LOG_BLOWUP;
 #[repr(C)] pub struct MlFri { _p: [u8; 0] }
 #[repr(C)] pub struct MlFriProof { _p: [u8; 0] }
 #[repr(C)] pub struct MlSumcheck { _p: [u8; 0] }
+#[repr(C)] pub struct MlWSumcheck { _p: [u8; 0] }
 #[repr(C)] pub struct MlPcsProof { _p: [u8; 0] }
 
 const _: () = assert!(std::mem::size_of::<Field128>() == 16 && std::mem::align_of::<Field128>() == 16);
@@ -52,6 +53,13 @@ extern "C" {
     pub fn ml_sumcheck_compute_polynomial(s: *mut MlSumcheck, total_degree: usize, previous_sum: *mut u8, t: *mut MlTranscript, nonzero: *mut u8, r: *mut u8) -> c_int;
     pub fn ml_sumcheck_fold(s: *mut MlSumcheck, r: *const u8) -> c_int;
     pub fn ml_sumcheck_free(s: *mut MlSumcheck);
+    // width-w tables (System path): the composition closure (sumcheck.rs:176) is passed as a sparse polynomial over the row
+    pub fn ml_wsumcheck_build(row_point: *const u8, n_vars: usize, matrix: *const u8, width: usize, height: usize, out: *mut *mut MlWSumcheck) -> c_int;
+    pub fn ml_wsumcheck_set_composition(w: *mut MlWSumcheck, n_terms: usize, coefs: *const u8, term_lens: *const u32, term_cols: *const u32) -> c_int;
+    pub fn ml_wsumcheck_partial_sum(w: *mut MlWSumcheck, r: *const u8, out: *mut u8) -> c_int;
+    pub fn ml_wsumcheck_fold(w: *mut MlWSumcheck, r: *const u8) -> c_int;
+    pub fn ml_wsumcheck_compute_polynomials(w: *mut MlWSumcheck, composition_degree: usize, t: *mut MlTranscript, sum: *const u8, coeffs: *mut u8, randoms: *mut u8) -> c_int;
+    pub fn ml_wsumcheck_free(w: *mut MlWSumcheck);
     pub fn ml_pcs_prove(inputs: *const u8, n_vars: usize, output: *const u8, evals: *const u8, n: usize, t: *mut MlTranscript, out: *mut *mut MlPcsProof) -> c_int;
     pub fn ml_pcs_proof_fri(p: *const MlPcsProof) -> *const MlFriProof;
     pub fn ml_pcs_proof_num_rounds(p: *const MlPcsProof) -> usize;
