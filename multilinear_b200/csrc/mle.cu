@@ -16,12 +16,18 @@ namespace mlb {
 
 static const int MLE_THREADS = 256;
 
-template <int NS, bool SUB>
+// Shared-memory slot of element m of a single-column tile (T = 1): 16-byte chunks XOR-swizzled inside each 128-byte line by the
+// line index (the SWIZZLE_128B pattern).  The last round of such a tile walks m = 8*lane + j, i.e. all lanes of a quarter-warp in
+// the same four banks (ncu: 28 M bank conflicts of 48 M wavefronts in the first pass); swizzled, the eight lanes land in eight
+// different bank groups, while consecutive-m accesses stay conflict-free (a permutation inside one line).
+__device__ __forceinline__ int mobius_swz(int m) { return m ^ ((m >> 3) & 7); }
+
+template <int NS, bool SUB, int NT = MLE_THREADS, bool SWZ = false>
 __device__ __forceinline__ void mobius_round(fe* data, int pitch, int log_r, int log_t, int q, int tid) {
     // bit-levels q .. q+NS-1 (counted from the top of the tile's R index), same item layout as the NTT rounds
     const int log_lr = log_r - q - NS;
     const int items = 1 << (log_r + log_t - NS);
-    for (int w = tid; w < items; w += MLE_THREADS) {
+    for (int w = tid; w < items; w += NT) {
         const int t = w & ((1 << log_t) - 1);
         const int rest = w >> log_t;
         const int l = rest & ((1 << log_lr) - 1);
@@ -29,7 +35,7 @@ __device__ __forceinline__ void mobius_round(fe* data, int pitch, int log_r, int
         const int m0 = (blk << (log_r - q)) + l;
         fe x[1 << NS];
 #pragma unroll
-        for (int j = 0; j < (1 << NS); j++) x[j] = data[(m0 + (j << log_lr)) * pitch + t];
+        for (int j = 0; j < (1 << NS); j++) x[j] = SWZ ? data[mobius_swz(m0 + (j << log_lr))] : data[(m0 + (j << log_lr)) * pitch + t];
 #pragma unroll
         for (int u = 0; u < NS; u++) {
             const int span = 1 << (NS - 1 - u);
@@ -40,12 +46,15 @@ __device__ __forceinline__ void mobius_round(fe* data, int pitch, int log_r, int
             }
         }
 #pragma unroll
-        for (int j = 0; j < (1 << NS); j++) data[(m0 + (j << log_lr)) * pitch + t] = x[j];
+        for (int j = 0; j < (1 << NS); j++) {
+            if (SWZ) data[mobius_swz(m0 + (j << log_lr))] = x[j];
+            else data[(m0 + (j << log_lr)) * pitch + t] = x[j];
+        }
     }
 }
 
 // tile = all 2^log_r values of index bits [bit_lo, bit_lo + log_r) x 2^log_t contiguous low indices
-template <bool SUB>
+template <bool SUB, bool SWZ>
 __global__ void __launch_bounds__(MLE_THREADS, 2) mobius_pass_kernel(const fe* __restrict__ in, fe* __restrict__ out, int log_r, int log_t,
                                                                      int bit_lo) {
     extern __shared__ uint4 smem_raw[];
@@ -64,25 +73,30 @@ __global__ void __launch_bounds__(MLE_THREADS, 2) mobius_pass_kernel(const fe* _
 #pragma unroll 8
     for (int idx = tid; idx < tile_elems; idx += MLE_THREADS) {
         const int t = idx & (T - 1), m = idx >> log_t;
-        data[m * pitch + t] = fe_load_nc(in + base + ((size_t)m << bit_lo) + t);
+        data[SWZ ? mobius_swz(m) : m * pitch + t] = fe_load_nc(in + base + ((size_t)m << bit_lo) + t);
     }
     __syncthreads();
     // the order of bit-levels is irrelevant (the per-bit updates commute)
     for (int q = 0; q < log_r;) {
         const int ns = log_r - q >= 3 ? 3 : log_r - q;
-        if (ns == 3) mobius_round<3, SUB>(data, pitch, log_r, log_t, q, tid);
-        else if (ns == 2) mobius_round<2, SUB>(data, pitch, log_r, log_t, q, tid);
-        else mobius_round<1, SUB>(data, pitch, log_r, log_t, q, tid);
+        if (ns == 3) mobius_round<3, SUB, MLE_THREADS, SWZ>(data, pitch, log_r, log_t, q, tid);
+        else if (ns == 2) mobius_round<2, SUB, MLE_THREADS, SWZ>(data, pitch, log_r, log_t, q, tid);
+        else mobius_round<1, SUB, MLE_THREADS, SWZ>(data, pitch, log_r, log_t, q, tid);
         q += ns;
         __syncthreads();
     }
 #pragma unroll 8
     for (int idx = tid; idx < tile_elems; idx += MLE_THREADS) {
         const int t = idx & (T - 1), m = idx >> log_t;
-        fe_store(out + base + ((size_t)m << bit_lo) + t, data[m * pitch + t]);
+        fe_store(out + base + ((size_t)m << bit_lo) + t, data[SWZ ? mobius_swz(m) : m * pitch + t]);
     }
 }
 
+// Measured and dropped (profiles/r1_mobius_notes.txt): a persistent one-CTA-per-SM variant with a three-stage shared-memory ring
+// fed by cp.async.bulk + mbarrier and drained by bulk stores.  It was correct but slower (0.514 ms vs 0.443 ms at 2^24): the
+// column passes need one bulk copy per 256 B - 1 KB row run, issued by one warp while the others wait at the barrier, and the
+// first pass was limited by shared-memory bank conflicts, not by load/compute/store serialisation.  The XOR swizzle above is
+// what moved the number (0.443 -> 0.349 ms).
 int mobius_launch(const fe* in, fe* out, size_t len, bool subtract, cudaStream_t s) {
     if (len == 0) return ML_OK;
     // the reference transforms only the first 2^trailing_zeros(len) entries (polynomials.rs:151-155)
@@ -93,8 +107,10 @@ int mobius_launch(const fe* in, fe* out, size_t len, bool subtract, cudaStream_t
         if (in != out) MLB_CUDA(cudaMemcpyAsync(out, in, 16, cudaMemcpyDeviceToDevice, s));
         return ML_OK;
     }
-    MLB_CUDA(cudaFuncSetAttribute(mobius_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-    MLB_CUDA(cudaFuncSetAttribute(mobius_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    MLB_CUDA(cudaFuncSetAttribute(mobius_pass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    MLB_CUDA(cudaFuncSetAttribute(mobius_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    MLB_CUDA(cudaFuncSetAttribute(mobius_pass_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    MLB_CUDA(cudaFuncSetAttribute(mobius_pass_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     ProfScope prof(PROF_MOBIUS, 32.0 * (double)span, s);
     int bit_lo = 0;
     const fe* src = in;
@@ -119,8 +135,11 @@ int mobius_launch(const fe* in, fe* out, size_t len, bool subtract, cudaStream_t
         const int pitch = T > 1 ? T + 1 : 1;
         const size_t smem = (size_t)R * pitch * 16;
         const size_t tiles = span >> (log_r + log_t);
-        if (subtract) mobius_pass_kernel<true><<<(unsigned)tiles, MLE_THREADS, smem, s>>>(src, out, log_r, log_t, bit_lo);
-        else mobius_pass_kernel<false><<<(unsigned)tiles, MLE_THREADS, smem, s>>>(src, out, log_r, log_t, bit_lo);
+        if (log_t == 0 && log_r >= 6) {  // single-column tile: swizzled shared-memory layout
+            if (subtract) mobius_pass_kernel<true, true><<<(unsigned)tiles, MLE_THREADS, smem, s>>>(src, out, log_r, log_t, bit_lo);
+            else mobius_pass_kernel<false, true><<<(unsigned)tiles, MLE_THREADS, smem, s>>>(src, out, log_r, log_t, bit_lo);
+        } else if (subtract) mobius_pass_kernel<true, false><<<(unsigned)tiles, MLE_THREADS, smem, s>>>(src, out, log_r, log_t, bit_lo);
+        else mobius_pass_kernel<false, false><<<(unsigned)tiles, MLE_THREADS, smem, s>>>(src, out, log_r, log_t, bit_lo);
         MLB_KERNEL_CHECK();
         src = out;
         bit_lo += log_r;
