@@ -274,6 +274,9 @@ int ml_ipc_open(const uint8_t handle[64], void **dev_out);
 int ml_ipc_close(void *dev);
 int ml_ipc_free(void *dev);
 
+/* host-side phase trace of the host-pointer prove path (recorded when MLB_TRACE is set in the environment); prints to stderr */
+void ml_trace_dump(void);
+
 /* ---- instrumentation for bench.py ----
  * ml_profile_*: when enabled, every kernel group is bracketed by CUDA events on its launch stream;
  * ml_profile_get sums device time, launches and algorithmic HBM bytes (input read once + output written once)

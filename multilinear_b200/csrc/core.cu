@@ -1,5 +1,9 @@
 // Context, memory and the array-level C ABI (field vectors, NTT, Reed-Solomon, multilinear transforms, transcript).
 #include <cstdlib>
+#include <utility>
+#include <cstring>
+#include <mutex>
+#include <map>
 #include "field.cuh"
 #include "handles.h"
 #include "internal.h"
@@ -68,10 +72,9 @@ int get_ctx(Ctx** out) {
         MLB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
         unsigned long long thr = ~0ull;  // keep freed scratch cached in the pool
         MLB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-        // Never satisfy an allocation on one stream with a block whose free is still queued on another stream: the driver
-        // does that by making the allocating stream wait for the other stream's pending work, which silently serialises
-        // concurrent commits (measured: 8 host-pointer commits in flight took 75-1000 ms per step depending on which
-        // block the allocator picked).  Completed frees are still reused; otherwise the pool grows.
+        // default pool (only used for the legacy stream now, see pool_for): never satisfy an allocation on one stream with a
+        // block whose free is still queued on another stream — the driver does that by making the allocating stream wait
+        // for the other stream's pending work, which silently serialises concurrent commits
         int off = 0;
         if (!getenv("MLB_POOL_INTERNAL_DEPS")) MLB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
         it = g_ctx.emplace(dev, c).first;
@@ -79,9 +82,42 @@ int get_ctx(Ctx** out) {
     *out = it->second;
     return ML_OK;
 }
+// One memory pool per (device, stream).  Concurrent commits run on their own streams and make ~100 stream-ordered allocations
+// each, up to 512 MB.  In the shared default pool a block freed on stream A and requested on stream B either makes B wait for
+// A's pending work (internal dependencies) or forces the pool to grow with slow virtual-memory calls under a driver-wide lock;
+// both showed up as erratic end-to-end times (75 ms to > 1 s per step with 8 commits in flight, tools/e2e_probe.py traces: every
+// thread stuck in cudaMallocAsync / kernel launches at once).  With a private pool per stream every block is recycled on the
+// stream that freed it: no cross-stream waits, and no growth after the first commit.
+static std::mutex g_pool_mu;
+static std::map<std::pair<int, cudaStream_t>, cudaMemPool_t> g_pools;
+static cudaMemPool_t pool_for(cudaStream_t s) {
+    static const bool shared = getenv("MLB_SHARED_POOL") != nullptr;
+    if (shared || s == nullptr) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    auto key = std::make_pair(dev, s);
+    auto it = g_pools.find(key);
+    if (it != g_pools.end()) return it->second;
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); pool = nullptr; }
+    if (pool) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    g_pools.emplace(key, pool);
+    return pool;
+}
 int dev_alloc_async(void** p, size_t bytes, cudaStream_t s) {
     if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMallocAsync(p, bytes, s);
+    cudaMemPool_t pool = pool_for(s);
+    cudaError_t e = pool ? cudaMallocFromPoolAsync(p, bytes, pool, s) : cudaMallocAsync(p, bytes, s);
     if (e != cudaSuccess) { set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); return ML_ERR_ALLOC; }
     return ML_OK;
 }

@@ -1,7 +1,11 @@
 // Handle-level C ABI: Merkle trees, FRI prover data and proofs, sumcheck tables, PCS / batched PCS provers.
 // Host code here is orchestration only (Fiat-Shamir transcript, 3-coefficient round polynomials, query
 // bookkeeping); every array operation is a CUDA kernel from the sibling translation units.
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include "field.cuh"
 #include "handles.h"
 #include "internal.h"
@@ -30,9 +34,46 @@ struct Scratch {
 int pmalloc(void** p, size_t bytes, cudaStream_t s) { return dev_alloc_async(p, bytes, s); }
 void pfree(void* p, cudaStream_t s) { if (p) cudaFreeAsync(p, s); }
 
+// ---- optional host-side phase trace (MLB_TRACE=1): (thread, tag, seconds) tuples dumped by ml_trace_dump()
+struct TraceRec { size_t tid; const char* tag; double t; };
+static std::mutex g_trace_mu;
+static std::vector<TraceRec> g_trace;
+static inline void trace(const char* tag) {
+    static const bool on = getenv("MLB_TRACE") != nullptr;
+    if (!on) return;
+    const double t = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    std::lock_guard<std::mutex> lock(g_trace_mu);
+    static std::atomic<size_t> next_id{0};
+    thread_local size_t my_id = next_id++;
+    g_trace.push_back(TraceRec{my_id, tag, t});
+}
+static void trace_dump_impl() {
+    std::lock_guard<std::mutex> lock(g_trace_mu);
+    if (g_trace.empty()) return;
+    const double t0 = g_trace.front().t;
+    for (const TraceRec& r : g_trace) fprintf(stderr, "TRACE %03zu %-14s %9.3f ms\n", r.tid, r.tag, (r.t - t0) * 1e3);
+    g_trace.clear();
+}
+static int stream_wait_blocking(cudaStream_t s);
+// Host -> device upload.  Large uploads from concurrent callers are serialised (one at a time, each waited for under the
+// lock): a copy engine shared by n uploads finishes all of them late, so n commits submitted together would all start their
+// NTT after the LAST byte of the LAST input arrived and then run in lock-step — copy phase with idle SMs, compute phase with an
+// idle copy engine (measured with 8 host-pointer commits in flight: 113-136 ms per step in lock-step, 75 ms when staggered).
+// One upload at a time makes the stagger structural: commit k computes while commit k+1 uploads.
+static std::mutex g_upload_mu;
 int h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
-    if (bytes) MLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
-    return ML_OK;
+    if (!bytes) return ML_OK;
+    if (bytes < ((size_t)16 << 20)) {
+        MLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+        return ML_OK;
+    }
+    trace("upload_wait");
+    std::lock_guard<std::mutex> lock(g_upload_mu);
+    trace("upload_begin");
+    MLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    int st = stream_wait_blocking(s);
+    trace("upload_done");
+    return st;
 }
 // Wait for a stream without spinning: the end-of-chain waits last milliseconds, and with several commits in flight per GPU
 // and one process per GPU the default spin-wait of cudaStreamSynchronize keeps (streams x GPUs) host cores busy — more than an
@@ -553,6 +594,7 @@ int fold_chain_dev(Ctx* ctx, ml_fri* f, BatchedFri* b, ml_sumcheck* sc, hfe prev
         MLB_TRY(chain_challenge_launch(tr_dev, layer_root_ptr(f->layers.back()), 32, roots_dev + 32 * (f->layers.size() - 1), r_dev, false, s));
     }
     // ---- single synchronisation point: roots, last element, status, coefficients, transcript
+    trace("enqueued");
     std::vector<uint8_t> host(off_part);
     MLB_TRY(d2h_sync(host.data(), base, off_part, s));
     int status = 0;
@@ -860,6 +902,7 @@ int bfri_verify_queries(const ml_bfri_proof* p, ml_transcript* t, const hfe* rs,
 }  // namespace
 
 extern "C" {
+void ml_trace_dump(void) { trace_dump_impl(); }
 
 // ================================================================== Merkle
 int ml_merkle_commit(const uint8_t* data, size_t item_bytes, size_t n_items, ml_merkle** out) {
@@ -1076,13 +1119,17 @@ int ml_fri_open_query_at(const ml_fri* f, size_t index, uint8_t* values, uint8_t
     return ML_OK;
 }
 static int fri_prove_from(Ctx* ctx, ml_fri* f, size_t n, ml_transcript* t, cudaStream_t s, ml_fri_proof** out) {
+    trace("chain_begin");
     int st = fold_chain_dev(ctx, f, nullptr, nullptr, 0, nullptr, 0, true, t, s);
+    trace("chain_done");
     ml_fri_proof* p = nullptr;
     if (st == ML_OK) {
         p = new ml_fri_proof();
         st = assemble_fri_proof(f, n, t, p, s);
     }
+    trace("queries_done");
     free_fri(f);
+    trace("freed");
     if (st != ML_OK) { delete p; return st; }
     *out = p;
     return ML_OK;
@@ -1135,10 +1182,13 @@ int ml_rs_fri_prove_dev(const void* coeffs_dev, size_t n, ml_transcript* t, void
 int ml_rs_fri_prove(const uint8_t* coeffs, size_t n, ml_transcript* t, ml_fri_proof** out) {
     API_BEGIN
     cudaStream_t s = lib_stream(ctx);
+    trace("call");
     Scratch d(s);
     MLB_TRY(d.alloc(n * 16));
     MLB_TRY(h2d(d.p, coeffs, n * 16, s));
-    return ml_rs_fri_prove_dev(d.p, n, t, s, out);
+    int st = ml_rs_fri_prove_dev(d.p, n, t, s, out);
+    trace("return");
+    return st;
 }
 int ml_fri_verify(const ml_fri_proof* p) {  // fri/mod.rs:287-309
     if (p->queries.size() != ML_NUM_QUERIES) return ML_V_WRONG_NUM_QUERIES;

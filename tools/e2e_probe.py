@@ -1,6 +1,10 @@
 """Diagnostic: end-to-end (host pointer) vs device-resident prove calls at several levels of concurrency."""
 import ctypes as C, json, os, sys, threading, time
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+MODE = sys.argv[1] if len(sys.argv) > 1 else "plain"
+if "torch" in MODE:
+    import torch
+    torch.cuda.init(); _x = torch.zeros(1, device="cuda"); torch.cuda.synchronize()
 from multilinear_b200 import api as ml
 from multilinear_b200 import load
 L = load()
@@ -31,8 +35,22 @@ def run(pe, steps, dev):
     for t in ts: t.join()
     ml.synchronize()
     return (time.perf_counter() - t0) / steps * 1e3, sum(times) / len(times) * 1e3
+if "prelude" in MODE:  # what bench.py does first: 6 device-resident commits in flight, 10 steps
+    def dev_worker(j):
+        ml.set_device(0)
+        for _ in range(10):
+            f = ml.FriProverData.fold_from_coeffs_dev(coeffs[j % 2], n, ml.Transcript(), streams[j].value); f.fold_roots(); del f
+    ts = [threading.Thread(target=dev_worker, args=(j,)) for j in range(6)]
+    for t in ts: t.start()
+    for t in ts: t.join()
+    ml.synchronize()
+if "events" in MODE:
+    e0 = torch.cuda.Event(enable_timing=True); e0.record()
 run(PEMAX, 1, False)
-for dev in (True, False, False, False):
-    for pe in ((1, 2, 4, 8) if dev else (4, 8, 8, 8)):
+print("MODE", MODE)
+L.ml_trace_dump.restype = None
+for dev in (False, False):
+    for pe in (8, 8, 8):
+        if os.environ.get("MLB_TRACE"): L.ml_trace_dump(); print("---- run", flush=True)
         step, call = run(pe, 3, dev)
         print("dev=%d PE=%d  step %.1f ms  (%.1f ms per commit)  call mean %.1f ms" % (dev, pe, step, step / pe, call), flush=True)
