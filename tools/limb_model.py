@@ -111,6 +111,51 @@ def reduce_wide(p):
     return v - M if v >= M else v
 
 
+K45 = 45 << 8  # c = 45*2^40 - 1 = K45 * 2^32 - 1
+
+
+def reduce_wide_v2(p):
+    """fe_reduce_wide_v2: hi*c = ((hi * 11520) << 32) - hi, twice, then one add of c that serves both the 2^128 wrap and
+    the conditional subtraction of M.  Mirrors the two carry-chained IMAD.WIDE rows and the add/sub chains of field.cuh."""
+    a = [p[0], p[1], p[2], p[3], 0, 0]
+    # row over the even limbs of hi (at limbs 1 and 3), then the odd limbs (at 2 and 4); the last madc cannot carry out
+    for start, (h0, h1) in ((1, (p[4], p[6])), (2, (p[5], p[7]))):
+        ch = Chain()
+        a[start] = ch.mad_lo(h0, K45, a[start], use_c=False)
+        a[start + 1] = ch.mad_hi(h0, K45, a[start + 1])
+        a[start + 2] = ch.mad_lo(h1, K45, a[start + 2])
+        top = (h1 * K45 >> 32) + ch.cf
+        assert top >> 32 == 0
+        a[start + 3] = top
+    assert val(a) == val(p[:4]) + ((val(p[4:]) * K45) << 32)
+    x, borrow = [], 0
+    for i in range(6):
+        d = a[i] - (p[4 + i] if i < 4 else 0) - borrow
+        borrow = 1 if d < 0 else 0
+        x.append(d & MASK)
+    assert borrow == 0 and val(x) == val(p[:4]) + val(p[4:]) * (C0 + (C1 << 32))
+    u = x[4] * K45 + (((x[5] * K45) & MASK) << 32)
+    assert x[5] * K45 <= MASK and u >> 64 == 0
+    ch = Chain()
+    b1 = ch.add(x[1], u & MASK, False, True)
+    b2 = ch.add(x[2], u >> 32, True, True)
+    b3 = ch.add(x[3], 0, True, True)
+    k1 = ch.cf
+    y, borrow = [], 0
+    for lhs, rhs in ((x[0], x[4]), (b1, x[5]), (b2, 0), (b3, 0)):
+        d = lhs - rhs - borrow
+        borrow = 1 if d < 0 else 0
+        y.append(d & MASK)
+    k2 = MASK if borrow else 0
+    assert (k1 + k2) & MASK in (0, 1)            # at most one net wrap of 2^128
+    z = val(y) + C0 + (C1 << 32)
+    carry = z >> 128
+    g = (k1 + k2 + carry) & MASK
+    if (k1 + k2) & MASK == 1:
+        assert carry == 0                        # a wrapped value is tiny: + c cannot carry again
+    return (z & (2**128 - 1)) if g else val(y)
+
+
 if __name__ == "__main__":
     random.seed(7)
     edge = [0, 1, 2, M - 1, M - 2, 2**64 - 1, 2**64, 2**127, 2**96 - 1, C0 + (C1 << 32), 2**128 - 2**46, M - 2**40]
@@ -121,10 +166,13 @@ if __name__ == "__main__":
         p = mul_wide(x, y)
         assert val(p) == x * y, (x, y)
         assert reduce_wide(p) == x * y % M, (x, y)
+        assert reduce_wide_v2(p) == x * y % M, (x, y)
     # reduce_wide must also be right for any 256-bit input (accumulator path)
     for _ in range(20000):
         v = random.getrandbits(256)
         assert reduce_wide(limbs(v, 8)) == v % M
+        assert reduce_wide_v2(limbs(v, 8)) == v % M
     for v in (2**256 - 1, 2**256 - 2**128, (M - 1) * (M - 1), 2**255):
         assert reduce_wide(limbs(v, 8)) == v % M
+        assert reduce_wide_v2(limbs(v, 8)) == v % M
     print("limb model ok")
