@@ -27,11 +27,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the group's largest launch, from the committed ncu captures:
-#   merkle_leaf_subtree (2^24 leaves): profiles/r1_ncu_merkle_dram_traffic_v4.csv  (920.6 MB read + 952.6 MB written)
-#   ntt_rs_encode: sum of the three passes in profiles/r1_ncu_top_kernels_v3.txt (1.881 GB read incl. the 512 MB
-#   twiddle matrix, 1.795 GB written) — the group is timed as one unit
-DRAM_TRAFFIC = {"merkle_leaf_subtree": 920619264 + 952640256, "ntt_rs_encode": 1881274000 + 1794676000}
+# dram__bytes_read.sum + dram__bytes_write.sum of the group's largest launch, from the committed ncu --set full capture
+# profiles/r1_ncu_top_kernels_v4.txt (second part):
+#   merkle_leaf_subtree (2^24 leaves): 889.8 MB read + 952.1 MB written (algorithmic: 1543.5 MB)
+#   ntt_rs_encode: sum of the three passes, 1881.4 MB read (incl. the 512 MB inter-pass twiddle matrix) + 1764.9 MB written —
+#   the group is timed as one unit (algorithmic: 805.3 MB; the two intermediate round trips are the four-step schedule)
+DRAM_TRAFFIC = {"merkle_leaf_subtree": 889808640 + 952099328, "ntt_rs_encode": 1881384448 + 1764900096}
 METRIC = "pcs_commit_melem_per_s"
 UNIT = "Melem/s"
 PROF_NAMES = ["ntt_rs_encode", "merkle_leaf_subtree", "merkle_nodes", "merkle_top", "fri_fold", "sumcheck_sums", "sumcheck_fold",
