@@ -11,6 +11,7 @@
 //   - every layer is still written to HBM (the prover opens paths from them), 32 B per digest, once;
 //   - upper layers repeat the same scheme on digests; the last <= 2048 nodes finish in one CTA.
 // All layers live in one buffer: layer l starts at digest index 2L - (2L >> l) (merkle_layer_offset).
+#include <cstring>
 #include "field.cuh"
 #include "internal.h"
 #include "sha256.cuh"
@@ -121,23 +122,54 @@ __global__ void __launch_bounds__(128) merkle_nodes_kernel(uint8_t* __restrict__
     subtree_walk<LOG_G, false>(nullptr, digests, n_leaves, from_layer, g << LOG_G);
 }
 
-// One CTA finishes the tree from a layer with <= 2 * blockDim.x * 4 nodes (loops otherwise).
-__global__ void __launch_bounds__(256) merkle_top_kernel(uint8_t* digests, size_t n_leaves, int from_layer) {
+// The last <= 4096 nodes of a tree: a chain of up to 12 dependent levels, too small for a grid and too much hashing for one
+// SM (2048 + 1024 + ... node hashes at ~2400 instructions each kept a single CTA busy for ~65 us, 14 trees per commit).
+// One thread-block cluster of 8 CTAs (8 SMs, 4096 threads) walks the levels with a cluster barrier between them: level data
+// goes through global memory (L2), made visible across the cluster's CTAs by __threadfence() before barrier.cluster.
+static const int TOP_CLUSTER = 8, TOP_THREADS = 512;
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__global__ void __launch_bounds__(TOP_THREADS) merkle_top_kernel(uint8_t* digests, size_t n_leaves, int from_layer) {
     size_t count = n_leaves >> from_layer;
     int layer = from_layer;
+    const size_t g = (size_t)cluster_cta_rank() * blockDim.x + threadIdx.x, stride = (size_t)TOP_CLUSTER * blockDim.x;
     while (count > 1) {
         const size_t next = count >> 1;
-        for (size_t i = threadIdx.x; i < next; i += blockDim.x) {
+        for (size_t i = g; i < next; i += stride) {
             uint32_t l[8], r[8], o[8];
             sha_load_digest(layer_ptr(digests, n_leaves, layer, 2 * i), l);
             sha_load_digest(layer_ptr(digests, n_leaves, layer, 2 * i + 1), r);
             sha256_node64(l, r, o);
             sha_store_digest(layer_ptr(digests, n_leaves, layer + 1, i), o);
         }
-        __syncthreads();
+        __threadfence();
+        cluster_sync_all();
         count = next;
         layer++;
     }
+}
+static int merkle_top_launch(uint8_t* digests, size_t n_leaves, int layer, cudaStream_t s) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(TOP_CLUSTER, 1, 1);
+    cfg.blockDim = dim3(TOP_THREADS, 1, 1);
+    cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = TOP_CLUSTER;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    MLB_CUDA(cudaLaunchKernelEx(&cfg, merkle_top_kernel, digests, n_leaves, layer));
+    return ML_OK;
 }
 
 // Batched leaves (Merkle::batch_commit, :110-116): leaf_i = SHA-256(pair_0(i) || pair_1(i) || ... || pair_{B-1}(i)).
@@ -201,7 +233,7 @@ static int upper_from(uint8_t* digests, size_t n_leaves, int from_layer, cudaStr
         size_t count = n_leaves >> layer;
         if (count <= 4096) {
             ProfScope prof(PROF_MERKLE_TOP, 64.0 * (double)count, s);
-            merkle_top_kernel<<<1, 256, 0, s>>>(digests, n_leaves, layer);
+            MLB_TRY(merkle_top_launch(digests, n_leaves, layer, s));
             MLB_KERNEL_CHECK();
             return ML_OK;
         }

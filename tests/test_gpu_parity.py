@@ -413,6 +413,47 @@ def test_wide_sumcheck_fold_random_and_errors(ml, oracle):
         ml.WideSumcheckTables.build(row_point, matrix[:w * 100], w)  # height not 2^n_vars
 
 
+def test_snark_test_system_sumcheck_then_pcs(ml, oracle):
+    """the reference's snark_test (src/fri/multilinear_pcs.rs:279-316): System sumcheck over a width-1 trace with the
+    zero constraint, then PCSProof::prove at the sumcheck's random point on the SAME transcript; the verifier replays the
+    sumcheck (verify_with_evaluations, sumcheck.rs:92-124) and verifies the PCS proof.  2^16 rows (the reference uses 2^20)."""
+    from test_oracle import PYTHAGOREAN
+    log_h = 16
+    rows = list(PYTHAGOREAN)
+    while len(rows) < 1 << log_h:
+        rows = rows + rows
+    evals = fe_arr(rows)                                   # Trace::new(trace, 1)
+    t, ot = ml.Transcript(), oracle.transcript()
+    c = ot.next_challenge()                                # ChallengeSet::new: every challenge equals this value
+    assert t.next_challenge() == c
+    row_point = fe_arr([c] * log_h)
+    terms = [(0, [])]                                      # constraint_mask = [1], Expr = 0, degree 1 (:262-267)
+    g = ml.WideSumcheckTables.build(row_point, evals, 1)
+    o = oracle.wsumcheck_build(row_point, evals, 1)
+    g.set_composition(terms)
+    o.set_composition(terms)
+    gp, grs = g.compute_sumcheck_polynomials(1, t, 0)
+    op, ors = o.compute_sumcheck_polynomials(1, ot, 0)
+    assert gp == op and grs == ors and not any(gp)
+    inputs = fe_arr(grs)
+    out = ml.MultilinearPolynomialEvals(evals).evaluate(grs)
+    assert out == oracle.mle_evals_evaluate(evals, inputs)
+    proof = ml.PCSProof.prove(inputs, out, evals, t)
+    oproof, st = oracle.pcs_prove(inputs, out, evals, ot)
+    assert st == 0 and proof.fri_proof.serialize() == oproof.fri.blob
+    assert t.random() == ot.random()
+    # verifier side: fresh transcript, replay the sumcheck absorbs / challenges, then the PCS verifier
+    vt = ml.Transcript()
+    assert vt.next_challenge() == c
+    pol_r = 0
+    for k in range(log_h):
+        for cf in gp[2 * k:2 * k + 2]:
+            vt.absorb(int(cf).to_bytes(16, "little"))
+        assert vt.next_challenge() == grs[k]
+    assert ml.delta_evaluate(row_point, inputs) * 0 % M == pol_r   # delta * composition == pol(r): 0 == 0
+    assert proof.verify(vt) == 0
+
+
 # ------------------------------------------------------------------ sharded batched commit (config 5), single GPU
 @pytest.mark.parametrize("mode", ["serial", "pipelined", "p2p"])
 def test_sharded_batch_commit_single_gpu(ml, oracle, mode):
