@@ -206,7 +206,22 @@ int ml_stream_create(void** out) {
     *out = (void*)s;
     return ML_OK;
 }
-int ml_stream_destroy(void* stream) { MLB_CUDA(cudaStreamDestroy((cudaStream_t)stream)); return ML_OK; }
+int ml_stream_destroy(void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    MLB_CUDA(cudaStreamSynchronize(s));
+    {   // drop the stream's private pool (the driver defers the release until its last allocation is freed)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        auto it = g_pools.find(std::make_pair(dev, s));
+        if (it != g_pools.end()) {
+            if (it->second) cudaMemPoolDestroy(it->second);
+            g_pools.erase(it);
+        }
+    }
+    MLB_CUDA(cudaStreamDestroy(s));
+    return ML_OK;
+}
 int ml_stream_synchronize(void* stream) { MLB_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return ML_OK; }
 int ml_set_thread_stream(void* stream, int enable) {
     tl_stream = (cudaStream_t)stream;
