@@ -88,6 +88,9 @@ int ml_fe_mul_vec(const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out);
 int ml_fe_inv_vec(const uint8_t *a, size_t n, uint8_t *out);                    /* inv(0) = 0 */
 int ml_fe_pow_vec(const uint8_t *a, const uint8_t exp_le[16], size_t n, uint8_t *out); /* NttField::pow, ntt/mod.rs:56-58 */
 int ml_fe_from_i64_vec(const int64_t *v, size_t n, uint8_t *out);               /* From<i64>, field.rs:150-154 */
+/* n 256-bit little-endian integers (32 bytes each) -> v mod M; variant selects the device reduction (1: multiply by the limbs
+ * of 2^128 - M, 2: shift form, the one every kernel uses) so the tests can drive both through adversarial inputs */
+int ml_fe_from_wide_vec(const uint8_t *v, size_t n, int variant, uint8_t *out);
 int ml_synthetic_elements_dev(uint64_t seed, size_t n, void *out_dev, void *stream); /* bench input generator */
 
 /* ---- NTT (src/ntt/mod.rs) ---- */

@@ -64,6 +64,17 @@ def _int(a):
     return int.from_bytes(np.ascontiguousarray(a).tobytes()[:16], "little")
 
 
+def from_wide(values, variant=2):
+    """256-bit integers -> v mod M through the device reduction (fe_reduce_wide_v1 / _v2)"""
+    vs = list(values)
+    buf = aligned_empty(32 * max(len(vs), 1))
+    for i, v in enumerate(vs):
+        buf[32 * i:32 * i + 32] = np.frombuffer(int(v).to_bytes(32, "little"), dtype=np.uint8)
+    out = elems_empty(len(vs))
+    check(load().ml_fe_from_wide_vec(_p(buf), _sz(len(vs)), C.c_int(variant), _p(out)))
+    return to_ints(out)
+
+
 def from_i64(values):
     """Field128::from(i64) for a list of ints (src/field.rs:150-154), on the GPU"""
     v = np.asarray(list(values), dtype=np.int64)

@@ -281,6 +281,16 @@ int ml_fe_from_i64_vec(const int64_t* v, size_t n, uint8_t* out) {
     MLB_TRY(fe_from_i64_launch(dv.as<int64_t>(), n, dout.as<fe>(), s));
     return download(out, dout.p, n * 16, s);
 }
+int ml_fe_from_wide_vec(const uint8_t* v, size_t n, int variant, uint8_t* out) {
+    API_BEGIN
+    if (variant != 1 && variant != 2) { set_error("reduction variant must be 1 or 2"); return ML_ERR_ARG; }
+    cudaStream_t s = lib_stream(ctx);
+    Scratch dv(s), dout(s);
+    MLB_TRY(upload(dv, v, n * 32, s));
+    MLB_TRY(dout.alloc(n * 16));
+    MLB_TRY(fe_from_wide_launch(dv.p, n, variant, dout.as<fe>(), s));
+    return download(out, dout.p, n * 16, s);
+}
 int ml_synthetic_elements_dev(uint64_t seed, size_t n, void* out_dev, void* stream) {
     API_BEGIN
     (void)ctx;

@@ -79,6 +79,25 @@ int fe_from_i64_launch(const int64_t* v, size_t n, fe* out, cudaStream_t s) {
     return ML_OK;
 }
 
+// 256-bit little-endian integers -> canonical elements (v mod M), with both reduction variants side by side: the entry point
+// behind ml_fe_from_wide_vec.  Used as hash-to-field for 32-byte digests and, in the tests, to drive fe_reduce_wide through
+// adversarial 256-bit patterns that products of canonical operands reach only with negligible probability.
+__global__ void fe_from_wide_kernel(const uint4* v, size_t n, int variant, fe* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        uint4 lo = v[2 * i], hi = v[2 * i + 1];
+        const uint32_t p[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        fe_store(out + i, variant == 1 ? fe_reduce_wide_v1(p) : fe_reduce_wide_v2(p));
+    }
+}
+int fe_from_wide_launch(const void* v, size_t n, int variant, fe* out, cudaStream_t s) {
+    if (n == 0) return ML_OK;
+    fe_from_wide_kernel<<<grid_for(n), 256, 0, s>>>((const uint4*)v, n, variant, out);
+    MLB_KERNEL_CHECK();
+    return ML_OK;
+}
+
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ull;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;

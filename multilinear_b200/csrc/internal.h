@@ -150,6 +150,7 @@ int bit_reverse_launch(const void* in, void* out, size_t n, size_t elem_bytes, c
 int fe_vec_launch(int op, const fe* a, const fe* b, size_t n, fe* out, cudaStream_t s);
 int fe_pow_vec_launch(const fe* a, hfe e, size_t n, fe* out, cudaStream_t s);
 int fe_from_i64_launch(const int64_t* v, size_t n, fe* out, cudaStream_t s);
+int fe_from_wide_launch(const void* v, size_t n, int variant, fe* out, cudaStream_t s);
 int synthetic_launch(uint64_t seed, size_t n, fe* out, cudaStream_t s);
 // mle.cu
 int mobius_launch(const fe* in, fe* out, size_t len, bool subtract, cudaStream_t s);

@@ -40,6 +40,31 @@ def test_field_mul_large_random(ml, oracle):
     assert np.array_equal(ml.mul(near, near[::-1].copy()), oracle.vec("mul", near, near[::-1].copy()))
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+def test_field_reduce_wide_adversarial(ml, variant):
+    """fe_reduce_wide on 256-bit patterns that exercise every carry / wrap path of both folds: all-ones limbs, low half
+    near 0 / near 2^128 / around M, high half tiny / huge, second-fold wrap candidates, plus random values"""
+    rng = random.Random(99 + variant)
+    two128, c = 1 << 128, (1 << 128) - M
+    los = [0, 1, 2, c - 1, c, c + 1, M - 1, M, M + 1, two128 - 1, two128 - 2, two128 - c, two128 - c - 1, two128 - (1 << 92), two128 - (1 << 46),
+           (1 << 96) - 1, (1 << 64), (1 << 32) - 1, 0xFFFFFFFF00000000FFFFFFFF00000000]
+    his = [0, 1, 2, 45, (1 << 14) - 1, (1 << 32) - 1, (1 << 32), (1 << 46) - 1, (1 << 64) - 1, (1 << 88) - 45, (1 << 96) - 1, M >> 1, M - 1, M,
+           two128 - 1, two128 - 2, two128 - (1 << 40), 0xFFFFFFFF00000000FFFFFFFF00000000, 0x00000000FFFFFFFF00000000FFFFFFFF]
+    vals = [(h << 128) | l for h in his for l in los]
+    # values whose first fold lands just below / above a multiple of 2^128 (wrap candidates of the second fold)
+    for h in his:
+        t = h * c
+        for d in (-2, -1, 0, 1, 2, c, -c):
+            l = (-(t) + d) % two128
+            vals.append((h << 128) | l)
+    vals += [(M - 1) ** 2, (M - 1) * (M - 2), (two128 - 1) ** 2 % (1 << 256), (1 << 256) - 1, (1 << 255), (1 << 256) - (1 << 128)]
+    vals += [rng.getrandbits(256) for _ in range(20000)]
+    vals += [(rng.getrandbits(128) << 128) | rng.choice([0, 1, two128 - 1, rng.getrandbits(20), two128 - 1 - rng.getrandbits(20)]) for _ in range(20000)]
+    got = ml.from_wide(vals, variant)
+    bad = [(hex(v), g) for v, g in zip(vals, got) if g != v % M]
+    assert not bad, bad[:3]
+
+
 def test_field_inv_pow_from_i64(ml, oracle):
     rng = random.Random(22)
     xs = EDGE + [rng.randrange(M) for _ in range(500)]
