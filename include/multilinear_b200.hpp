@@ -243,6 +243,60 @@ class FriProof {
     ml_fri_proof* h_ = nullptr;
 };
 
+// src/constraint_system/sumcheck.rs:10-15 — SumcheckTables of arbitrary trace width (System::build_tables :22-38).
+// The composition the reference passes as a closure (:176) is a list of terms: comp(x) = sum_t coef_t * prod_k x[cols_t[k]].
+struct CompositionTerm {
+    F coef;
+    std::vector<uint32_t> cols;
+};
+struct SumcheckPolynomial {
+    std::vector<F> nonzero_coeffs;  // :17-19
+};
+class SumcheckTables {
+  public:
+    static SumcheckTables build(const std::vector<F>& row_point, const std::vector<F>& matrix, size_t width) {
+        SumcheckTables t;
+        check(ml_wsumcheck_build(raw(row_point), row_point.size(), raw(matrix), width, matrix.size() / width, &t.h_));
+        return t;
+    }
+    SumcheckTables(SumcheckTables&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    ~SumcheckTables() { if (h_) ml_wsumcheck_free(h_); }
+    void set_composition(const std::vector<CompositionTerm>& terms) {
+        std::vector<F> coefs;
+        std::vector<uint32_t> lens, cols;
+        for (auto& t : terms) {
+            coefs.push_back(t.coef);
+            lens.push_back((uint32_t)t.cols.size());
+            cols.insert(cols.end(), t.cols.begin(), t.cols.end());
+        }
+        if (cols.empty()) cols.push_back(0);
+        check(ml_wsumcheck_set_composition(h_, terms.size(), raw(coefs), lens.data(), cols.data()));
+    }
+    size_t height() const { return ml_wsumcheck_height(h_); }
+    F partial_sum(F r) {  // :204-232
+        F out;
+        check(ml_wsumcheck_partial_sum(h_, r.bytes(), out.bytes()));
+        return out;
+    }
+    void fold(F r) { check(ml_wsumcheck_fold(h_, r.bytes())); }  // :234-247
+    // :147-172 — returns (polynomials, randoms)
+    std::pair<std::vector<SumcheckPolynomial>, std::vector<F>> compute_sumcheck_polynomials(size_t composition_degree, Transcript& t, F sum) {
+        size_t rounds = 0;
+        for (size_t h = height(); h > 1; h >>= 1) rounds++;
+        const size_t td = composition_degree + 1;
+        std::vector<F> coeffs(rounds * td + 1), randoms(rounds + 1);
+        check(ml_wsumcheck_compute_polynomials(h_, composition_degree, t.handle(), sum.bytes(), raw(coeffs), raw(randoms)));
+        std::vector<SumcheckPolynomial> pols(rounds);
+        for (size_t k = 0; k < rounds; k++) pols[k].nonzero_coeffs.assign(coeffs.begin() + k * td, coeffs.begin() + (k + 1) * td);
+        randoms.resize(rounds);
+        return {std::move(pols), std::move(randoms)};
+    }
+
+  private:
+    SumcheckTables() = default;
+    ml_wsumcheck* h_ = nullptr;
+};
+
 // src/fri/multilinear_pcs.rs:79-191
 class PCSProof {
   public:

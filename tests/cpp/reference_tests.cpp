@@ -117,11 +117,86 @@ static void batched_pcs_verify_test() {
     EXPECT(proof.verify(vt) == 0);
 }
 
+// ---- field helpers for the verifier-side equations (one-element calls into the library; the host mirror has no arithmetic)
+static F fadd(F a, F b) { F o; check(ml_fe_add_vec(a.bytes(), b.bytes(), 1, o.bytes())); return o; }
+static F fsub(F a, F b) { F o; check(ml_fe_sub_vec(a.bytes(), b.bytes(), 1, o.bytes())); return o; }
+static F fmul(F a, F b) { F o; check(ml_fe_mul_vec(a.bytes(), b.bytes(), 1, o.bytes())); return o; }
+static F finv(F a) { F o; check(ml_fe_inv_vec(a.bytes(), 1, o.bytes())); return o; }
+static F poly_eval(const std::vector<F>& c, F x) {
+    F acc = F::from(0);
+    for (size_t i = c.size(); i-- > 0;) acc = fadd(fmul(acc, x), c[i]);
+    return acc;
+}
+// SumcheckPolynomial::to_polynomial (sumcheck.rs:269-276)
+static std::vector<F> to_polynomial(const SumcheckPolynomial& p, F sum) {
+    F s = F::from(0);
+    for (F c : p.nonzero_coeffs) s = fadd(s, c);
+    std::vector<F> coeffs{fmul(fsub(sum, s), finv(F::from(2)))};
+    coeffs.insert(coeffs.end(), p.nonzero_coeffs.begin(), p.nonzero_coeffs.end());
+    return coeffs;
+}
+// src/constraint_system/sumcheck.rs:342-365 — sumcheck_test: pythagorean trace (16 x 4), two constraints, sum 0,
+// checked with verify_sumcheck_debug (:55-90)
+static void sumcheck_test() {
+    const long long rows[64] = {3, 4, 5, 7, 5, 12, 13, 17, 8, 15, 17, 23, 7, 24, 25, 31, 20, 21, 29, 41, 12, 35, 37, 47, 9, 40, 41, 49, 28, 45, 53, 73,
+                                11, 60, 61, 71, 16, 63, 65, 79, 33, 56, 65, 89, 48, 55, 73, 103, 13, 84, 85, 97, 36, 77, 85, 113, 39, 80, 89, 119,
+                                65, 72, 97, 137};
+    const size_t width = 4, height = 16, n_vars = 4;
+    std::vector<F> matrix;
+    for (long long v : rows) matrix.push_back(F::from(v));
+    Transcript transcript;
+    // System::prover -> ChallengeSet::new (system.rs:132-147): the transcript is not mutated, so every challenge is the same value
+    F c = transcript.next_challenge();
+    std::vector<F> row_point(n_vars, c);
+    // constraint_mask (system.rs:91-93) over one constraint variable: [1 - c, c]
+    F m0 = fsub(F::from(1), c), m1 = c, zero = F::from(0);
+    // pythagorean_set (:333-339): mask0 * (x0^2 + x1^2 - x2^2) + mask1 * (x0 + x1 - x3), degree 2
+    std::vector<CompositionTerm> terms = {{m0, {0, 0}}, {m0, {1, 1}}, {fsub(zero, m0), {2, 2}}, {m1, {0}}, {m1, {1}}, {fsub(zero, m1), {3}}};
+    auto comp = [&](const std::vector<F>& x) {
+        F acc = F::from(0);
+        for (auto& t : terms) {
+            F p = t.coef;
+            for (uint32_t j : t.cols) p = fmul(p, x[j]);
+            acc = fadd(acc, p);
+        }
+        return acc;
+    };
+    Transcript verifier_transcript(transcript);
+    SumcheckTables tables = SumcheckTables::build(row_point, matrix, width);
+    tables.set_composition(terms);
+    F sum = F::from(0);
+    auto [pols, randoms] = tables.compute_sumcheck_polynomials(2, transcript, sum);
+    EXPECT(pols.size() == n_vars && pols[0].nonzero_coeffs.size() == 3 && tables.height() == 1);
+    // verify_sumcheck_debug
+    std::vector<F> rs;
+    for (F cf : pols[0].nonzero_coeffs) verifier_transcript.absorb(cf.bytes(), 16);
+    std::vector<F> pol = to_polynomial(pols[0], sum);
+    for (size_t k = 1; k < pols.size(); k++) {
+        F r = verifier_transcript.next_challenge();
+        for (F cf : pols[k].nonzero_coeffs) verifier_transcript.absorb(cf.bytes(), 16);
+        pol = to_polynomial(pols[k], poly_eval(pol, r));
+        rs.push_back(r);
+    }
+    F r = verifier_transcript.next_challenge();
+    rs.push_back(r);
+    EXPECT(rs == randoms);
+    std::vector<F> output(width);  // Trace::evaluate (evaluation.rs:33-48): the multilinear extension of every column at rs
+    for (size_t j = 0; j < width; j++) {
+        std::vector<F> col(height);
+        for (size_t i = 0; i < height; i++) col[i] = matrix[i * width + j];
+        output[j] = MultilinearPolynomialEvals{col}.evaluate(rs);
+    }
+    F delta;
+    check(ml_delta_evaluate(raw(row_point), raw(rs), n_vars, delta.bytes()));
+    EXPECT(fmul(delta, comp(output)) == poly_eval(pol, r));  // "Does not match polynomial evaluation"
+}
+
 int main() {
     struct { const char* name; void (*fn)(); } tests[] = {
         {"intt_test", intt_test}, {"merkle_test", merkle_test}, {"batched_merkle_test", batched_merkle_test},
         {"multilinear_conversion_test", multilinear_conversion_test}, {"prove_and_verify_test", prove_and_verify_test},
-        {"multilinear_pcs_bench_test", multilinear_pcs_bench_test}, {"batched_pcs_verify_test", batched_pcs_verify_test}};
+        {"multilinear_pcs_bench_test", multilinear_pcs_bench_test}, {"batched_pcs_verify_test", batched_pcs_verify_test},
+        {"sumcheck_test", sumcheck_test}};
     for (auto& t : tests) {
         int before = failures;
         try {
