@@ -59,10 +59,11 @@ __global__ void __launch_bounds__(256) fri_fold_chunk_kernel(const fe* __restric
         c1[tid] = fe_mul(base, fe_load_nc(hi + (H - 1)));
     }
     __syncthreads();
+    // half_n is a multiple of FOLD_SPAN (checked at launch), so there is no bounds test and the loads of four iterations
+    // (8 independent 16-byte loads per thread) can be issued back to back
 #pragma unroll 4
     for (int u = 0; u < FOLD_SPAN / 256; u++) {
         const size_t i = i0 + tid + 256 * u;
-        if (i >= half_n) break;
         fe a = fe_load_nc(cur + i), b = fe_load_nc(cur + i + half_n);
         fe even = fe_half(fe_add(a, b));
         const unsigned x = (unsigned)((i << k) & (((size_t)1 << LO_BITS) - 1));
@@ -90,7 +91,7 @@ int fri_fold_launch(Ctx* ctx, const fe* cur, size_t n_cur, fe* next, hfe r, cons
     MLB_TRY(get_root_tables(ctx, log_n0, s, &rt));
     const size_t half_n = n_cur / 2;
     ProfScope prof(PROF_FRI_FOLD, 24.0 * (double)n_cur, s);  // read n elements, write n/2
-    if ((int)k <= FOLD_MAX_K && log_n0 > LO_BITS && half_n >= (size_t)FOLD_SPAN && (half_n << k) <= ((size_t)1 << (log_n0 - 1)))
+    if ((int)k <= FOLD_MAX_K && log_n0 > LO_BITS && half_n >= (size_t)FOLD_SPAN && half_n % FOLD_SPAN == 0 && (half_n << k) <= ((size_t)1 << (log_n0 - 1)))
         fri_fold_chunk_kernel<<<(unsigned)((half_n + FOLD_SPAN - 1) / FOLD_SPAN), 256, 0, s>>>(cur, half_n, next, to_dev_fe(hfe_half(r)), r_dev, (int)k,
                                                                                                  log_n0, rt->lo, rt->hi);
     else
