@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(128, MINB) mb_sha_kernel(uint32_t* out, int it
     if (h[0] == 0x12345678u && h[7] == 0x9abcdef0u) out[tid] = h[3];
 }
 // raw pipe throughput: MODE 0 IADD3, 1 IMAD (32-bit), 2 IMAD.WIDE, 3 SHF (funnel shift), 4 LOP3, 5 IADD3+IMAD 1:1,
-// 6 SHF+IMAD 1:1, 7 SHF+IMAD.WIDE 1:1, 8 SHF+LOP3 1:1, 9 SHF+LOP3+IMAD 1:1:1
+// 6 SHF+IMAD 1:1, 7 SHF+IMAD.WIDE 1:1, 8 SHF+LOP3 1:1, 9 SHF+LOP3+IMAD 1:1:1, 10 IMAD.HI, 11 IMAD.HI+SHF,
+// 12 DFMA (fp64 pipe), 13 DFMA+IMAD.WIDE 1:1, 14 DFMA+SHF 1:1
 template <int MODE>
 __global__ void __launch_bounds__(256) mb_pipe_kernel(uint32_t* out, int iters, uint32_t seed) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,12 +65,18 @@ __global__ void __launch_bounds__(256) mb_pipe_kernel(uint32_t* out, int iters, 
 #pragma unroll
     for (int i = 0; i < 8; i++) { a[i] = seed + tid * 8 + i; b[i] = seed ^ (tid + 77 * i); wd[i] = a[i]; }
     uint32_t m = seed | 1u;
+    double fd[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) fd[i] = 1.0 + 1e-9 * (double)(tid + i);
+    const double fm = 1.0000001, fa = 1e-12;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             if (MODE == 0 || MODE == 5) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i]));
             if (MODE == 1 || MODE == 5 || MODE == 6 || MODE == 9) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(b[i]) : "r"(m), "r"(a[i]));
-            if (MODE == 2 || MODE == 7) asm volatile("{\n\t.reg .u32 lo;\n\tcvt.u32.u64 lo, %0;\n\tmad.wide.u32 %0, lo, %1, %0;\n\t}" : "+l"(wd[i]) : "r"(m));
+            if (MODE == 12 || MODE == 13 || MODE == 14) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(fd[i]) : "d"(fm), "d"(fa));
+            if (MODE == 14) asm volatile("shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(a[i]));
+            if (MODE == 2 || MODE == 7 || MODE == 13) asm volatile("{\n\t.reg .u32 lo;\n\tcvt.u32.u64 lo, %0;\n\tmad.wide.u32 %0, lo, %1, %0;\n\t}" : "+l"(wd[i]) : "r"(m));
             if (MODE == 10 || MODE == 11) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(b[i]) : "r"(m));
             if (MODE == 11) asm volatile("shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(a[i]));
             if (MODE == 3 || MODE == 6 || MODE == 7 || MODE == 8 || MODE == 9) asm volatile("shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(a[i]));
@@ -78,7 +85,7 @@ __global__ void __launch_bounds__(256) mb_pipe_kernel(uint32_t* out, int iters, 
     }
     uint32_t r = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) r += a[i] + b[i] + (uint32_t)wd[i] + (uint32_t)(wd[i] >> 32);
+    for (int i = 0; i < 8; i++) r += a[i] + b[i] + (uint32_t)wd[i] + (uint32_t)(wd[i] >> 32) + (uint32_t)__double2uint_rz(fd[i]);
     if (r == 0x12345678u) out[tid] = r;
 }
 
@@ -143,6 +150,9 @@ extern "C" int ml_microbench(const char* what, size_t n, int iters, double* ms_o
                 case 8: mb_pipe_kernel<8><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
                 case 10: mb_pipe_kernel<10><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
                 case 11: mb_pipe_kernel<11><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
+                case 12: mb_pipe_kernel<12><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
+                case 13: mb_pipe_kernel<13><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
+                case 14: mb_pipe_kernel<14><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
                 default: mb_pipe_kernel<9><<<gb, 256, 0, s>>>((uint32_t*)buf, iters, 0x1234567u); break;
             }
         }
@@ -164,7 +174,7 @@ extern "C" int ml_microbench(const char* what, size_t n, int iters, double* ms_o
     else if (w == "copy") *work_out = 2.0 * (double)n;
     else if (w.rfind("pipe", 0) == 0) {
         const int mode = atoi(what + 4);
-        const int per = (mode <= 4 || mode == 10) ? 1 : (mode == 9 ? 3 : 2);
+        const int per = (mode <= 4 || mode == 10 || mode == 12) ? 1 : (mode == 9 ? 3 : 2);
         *work_out = (double)n * iters * 8 * per;  // thread-instructions
     }
     else *work_out = (double)n * iters;
