@@ -34,12 +34,13 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = _nvcc()
+    extra = os.environ.get("MLB_EXTRA_NVCC_FLAGS", "").split()  # experiments only (e.g. -DMLB_MERKLE_LEAF_SPECIALISED)
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

@@ -34,6 +34,9 @@ __device__ __forceinline__ uint8_t* layer_ptr(uint8_t* digests, size_t n_leaves,
 // the G layers above them with a G-deep digest stack.  The walk is written as ONE loop whose body holds a single
 // inlined copy of the compression function (37 KB of straight-line SASS): unrolling the 2^(G+1)-1 hashes instead
 // makes a ~450 KB body that thrashes the instruction cache (ncu: stall_no_instruction dominant, profiles/r1_*).
+// Even one extra copy costs more than it saves: a second, leaf-specialised compression (padding words as constants, 8 %
+// fewer instructions per leaf hash) grew the body from 41 KB to 65 KB and made the 2^24-leaf launch 14 % SLOWER (5.91 -> 6.75 ms
+// per commit for the group, measured in the second session).
 // Control flow depends only on (j, lvl), identical for every thread, so there is no divergence; the stack is
 // indexed dynamically and lives in local memory (32 bytes of traffic per 2400-instruction hash).
 static const int MERKLE_THREADS = 128;
