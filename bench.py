@@ -358,7 +358,12 @@ def run_ours(args):
 
     batched = None
     if not args.no_batched:
-        batched = run_batched_commit(torch, ml, L, dist, world, rank, args.batched_polys, args.batched_log_n)
+        # secondary leg: never let it take the headline line down (e.g. a box without peer access between two GPUs);
+        # every rank takes the same branch because the failure modes are collective (IPC mapping, NCCL)
+        try:
+            batched = run_batched_commit(torch, ml, L, dist, world, rank, args.batched_polys, args.batched_log_n)
+        except Exception as e:  # noqa: BLE001
+            batched = {"workload": "batched_commit_%dx2^%d" % (args.batched_polys, args.batched_log_n), "error": str(e)[:300]}
 
     # max over ranks
     if dist is not None:
