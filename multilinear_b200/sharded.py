@@ -91,16 +91,25 @@ class CudaBackend:
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
         allh = [torch.empty(64, dtype=torch.uint8, device=self.device) for _ in range(world)]
         dist.all_gather(allh, mine)
-        bases = []
+        bases, ok = [], 1
         for g in range(world):
             if g == rank:
                 bases.append(own.value)
             else:
                 hb = (C.c_uint8 * 64)(*allh[g].cpu().tolist())
                 p = C.c_void_p()
-                self.api.check(self.L.ml_ipc_open(hb, C.byref(p)))
-                bases.append(p.value)
+                if self.L.ml_ipc_open(hb, C.byref(p)) != 0:  # no peer access to that GPU from here
+                    ok = 0
+                    bases.append(None)
+                else:
+                    bases.append(p.value)
+        # every rank must take the same path: agree on whether all mappings exist
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         self._peer = (key, own.value, bases, rank)
+        if int(flag[0]) == 0:
+            self.release_peer_buffers()
+            return None, None
         return own.value, bases
 
     def release_peer_buffers(self):
@@ -109,7 +118,7 @@ class CudaBackend:
         _, own, bases, rank = self._peer
         torch.cuda.synchronize()
         for g, b in enumerate(bases):
-            if g != rank:
+            if g != rank and b is not None:
                 self.L.ml_ipc_close(C.c_void_p(b))
         self.L.ml_ipc_free(C.c_void_p(own))
         self._peer = None
@@ -173,6 +182,9 @@ def sharded_batch_commit(local_evals, n, n_polys, backend, dist=None, mode="seri
     main = torch.cuda.current_stream() if cuda else None
     if mode == "p2p":
         own, bases = backend.peer_buffers(n_polys * chunk, dist)
+        if own is None:  # some pair of GPUs has no peer access: every rank falls back to the NCCL exchange
+            mode = "pipelined"
+    if mode == "p2p":
         codes = [backend.empty(32 * n) for _ in range(2)]
         freed = [None, None]  # event: the store pass has finished reading code buffer b
         for pl, ev in enumerate(local_evals):
