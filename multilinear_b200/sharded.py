@@ -38,7 +38,7 @@ class CudaBackend:
         self.api, self.L = api, load()
         self.device = torch.device("cuda", torch.cuda.current_device())
         self._side = None
-        self._peer = None  # (key, own_ptr, [mapped base per rank])
+        self._peer = None  # (key, own_ptr, [mapped base per rank], rank)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
