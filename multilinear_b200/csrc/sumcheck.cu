@@ -92,17 +92,32 @@ __global__ void __launch_bounds__(SC_THREADS) sumcheck_fold_sums_kernel(fe* __re
     acc_zero(a2);
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    // software pipeline: the eight loads of the next quad are issued before the six multiplies of the current one, so the
+    // memory system always has a full set of requests per thread in flight (the kernel is HBM-bound: 192 B per 6 multiplies)
+    fe c[8];
+    if (i < q) {
+        c[0] = fe_load(m + i); c[1] = fe_load(m + i + q); c[2] = fe_load(m + i + off); c[3] = fe_load(m + i + off + q);
+        c[4] = fe_load(d + i); c[5] = fe_load(d + i + q); c[6] = fe_load(d + i + off); c[7] = fe_load(d + i + off + q);
+    }
     for (; i < q; i += stride) {
-        fe m00 = fe_load(m + i), m01 = fe_load(m + i + q), m10 = fe_load(m + i + off), m11 = fe_load(m + i + off + q);
-        fe d00 = fe_load(d + i), d01 = fe_load(d + i + q), d10 = fe_load(d + i + off), d11 = fe_load(d + i + off + q);
-        fe m0 = fe_add(m00, fe_mul(r, fe_sub(m10, m00))), m1 = fe_add(m01, fe_mul(r, fe_sub(m11, m01)));
-        fe d0 = fe_add(d00, fe_mul(r, fe_sub(d10, d00))), d1 = fe_add(d01, fe_mul(r, fe_sub(d11, d01)));
+        const size_t nx = i + stride;
+        fe x[8];
+        if (nx < q) {
+            x[0] = fe_load(m + nx); x[1] = fe_load(m + nx + q); x[2] = fe_load(m + nx + off); x[3] = fe_load(m + nx + off + q);
+            x[4] = fe_load(d + nx); x[5] = fe_load(d + nx + q); x[6] = fe_load(d + nx + off); x[7] = fe_load(d + nx + off + q);
+        }
+        fe m0 = fe_add(c[0], fe_mul(r, fe_sub(c[2], c[0]))), m1 = fe_add(c[1], fe_mul(r, fe_sub(c[3], c[1])));
+        fe d0 = fe_add(c[4], fe_mul(r, fe_sub(c[6], c[4]))), d1 = fe_add(c[5], fe_mul(r, fe_sub(c[7], c[5])));
         fe_store(m + i, m0);
         fe_store(m + i + q, m1);
         fe_store(d + i, d0);
         fe_store(d + i + q, d1);
         acc_mul_add(a1, m1, d1);
         acc_mul_add(a2, fe_sub(fe_add(m1, m1), m0), fe_sub(fe_add(d1, d1), d0));
+        if (nx < q) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) c[k] = x[k];
+        }
     }
     fe s1 = block_sum(acc_reduce(a1), scratch);
     fe s2 = block_sum(acc_reduce(a2), scratch);
@@ -234,7 +249,9 @@ int sumcheck_partial_sum_launch(Ctx* ctx, const fe* m, const fe* d, size_t heigh
 int sumcheck_fold_sums_launch(fe* m, fe* d, size_t height, const fe* r_dev, fe* partials, int* n_blocks, cudaStream_t s) {
     const size_t off = height >> 1;
     if (off < 2) { set_error("sumcheck_fold_sums: height must be at least 4"); return ML_ERR_SIZE; }
-    const unsigned nb = blocks_for(off >> 1);
+    // 128 registers per thread: two CTAs are resident per SM, so the grid is exactly one persistent wave (148 x 2)
+    unsigned nb = blocks_for(off >> 1);
+    if (nb > 148 * 2) nb = 148 * 2;
     ProfScope prof(PROF_SUMCHECK_FOLD, 48.0 * (double)height, s);  // read 2 tables (h), write 2 half tables; the sums ride along
     sumcheck_fold_sums_kernel<<<nb, SC_THREADS, 0, s>>>(m, d, off, r_dev, partials);
     MLB_KERNEL_CHECK();
