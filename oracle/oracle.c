@@ -1031,7 +1031,7 @@ static void bfri_free(bfri_t *b) { if (b) { or_merkle_free(b->batch_layer); or_f
 static bfri_t *bfri_init(const uint8_t *const *codes, size_t n_codes, size_t n, or_transcript *t) {
     if (n_codes == 0 || !is_pow2(n) || n < 2) return NULL;
     size_t half = n / 2;
-    uint8_t **pairs = (uint8_t **)malloc(n_codes * sizeof(uint8_t *));
+    uint8_t **pairs = (uint8_t **)calloc(n_codes, sizeof(uint8_t *));
     for (size_t j = 0; j < n_codes; j++) { /* :62-74 */
         const fe *code = (const fe *)codes[j];
         fe *pj = (fe *)malloc((2 * half + 1) * sizeof(fe));
