@@ -577,3 +577,14 @@ def test_cpp_reference_tests(ml):
     p = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "all reference tests passed" in p.stdout
+
+
+def test_c_example_pcs_prove(ml, golden):
+    """examples/pcs_prove.c (plain C11 over the C ABI): the PCS golden vector at n_vars = 8 and an accepted proof"""
+    import subprocess
+    import __graft_entry__ as g
+    exe = g.build_c_example()
+    p = subprocess.run([exe, "8"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "root_0 623d135873c76f2306354b0d146b44c42c649d3060eaa022b0c0a96a4e051de2" in p.stdout   # SURVEY.md §8c PCS vector
+    assert "accepted" in p.stdout
