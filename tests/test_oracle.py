@@ -296,3 +296,45 @@ def test_wide_sumcheck_width1_equals_pcs_tables(oracle):
     b.set_composition([(1, [0])])
     assert a.partial_sum(2) == b.partial_sum(2) and a.partial_sum(1) == b.partial_sum(1)
     assert a.compute_sumcheck_polynomials(1, oracle.transcript(), claim) == b.compute_sumcheck_polynomials(1, oracle.transcript(), claim)
+
+
+def test_wide_sumcheck_matches_python_restatement(oracle):
+    """independent big-int restatement of partial_sum / fold (sumcheck.rs:204-247) for a width-3 trace, degree-3 composition"""
+    rng = random.Random(4)
+    nv, w = 4, 3
+    h = 1 << nv
+    mat = [rng.randrange(M) for _ in range(h * w)]
+    pts = [rng.randrange(M) for _ in range(nv)]
+    terms = [(rng.randrange(M), [0, 1, 2]), (rng.randrange(M), [2, 2]), (rng.randrange(M), []), (M - 1, [1])]
+    delta = []
+    for idx in range(h):  # Mask::evaluate (evaluation.rs:56-73), big-endian variable order
+        prod = 1
+        for i in range(nv):
+            p = pts[nv - 1 - i]
+            prod = prod * (p if (idx >> i) & 1 else (1 - p)) % M
+        delta.append(prod)
+    s = oracle.wsumcheck_build(fe_arr(pts), fe_arr(mat), w)
+    s.set_composition(terms)
+    assert fe_ints(s.tables()[1]) == delta
+    height = h
+    for r in (1, 2, 3, rng.randrange(M)):
+        off = height >> 1
+        want = 0
+        for i in range(off):
+            if r == 1:
+                d = delta[i + off]
+                row = [mat[(i + off) * w + j] for j in range(w)]
+            else:
+                d = ((1 - r) * delta[i] + r * delta[i + off]) % M
+                row = [((1 - r) * mat[i * w + j] + r * mat[(i + off) * w + j]) % M for j in range(w)]
+            want = (want + eval_terms(terms, row) * d) % M
+        assert s.partial_sum(r) == want
+        # fold with the same r
+        s.fold(r)
+        for i in range(off):
+            delta[i] = ((1 - r) * delta[i] + r * delta[i + off]) % M
+            for j in range(w):
+                mat[i * w + j] = ((1 - r) * mat[i * w + j] + r * mat[(i + off) * w + j]) % M
+        height = off
+        m_now, d_now = s.tables()
+        assert fe_ints(d_now) == delta[:height] and fe_ints(m_now) == mat[:height * w]
