@@ -1416,7 +1416,13 @@ int ml_wsumcheck_compute_polynomials(ml_wsumcheck* w, size_t composition_degree,
     hfe prev = hfe_load(sum);
     std::vector<hfe> evals(td + 1), coeffs;
     for (size_t k = 0; k < rounds; k++) {
-        for (size_t i = 1; i <= td; i++) MLB_TRY(wpartial(w, hfe_new((hfe)i), &evals[i]));  // :185-187
+        // :185-187 — every point of the round in one pass when td <= 4, else one pass per point
+        if (w->height >= 2 && td <= 4) {
+            MLB_TRY(wsumcheck_points_launch(w->matrix, w->delta, w->height, w->width, w->coef, w->len, w->off, w->cols, w->n_terms, w->n_cols,
+                                            (int)td, &evals[1], w->stream));
+        } else {
+            for (size_t i = 1; i <= td; i++) MLB_TRY(wpartial(w, hfe_new((hfe)i), &evals[i]));
+        }
         evals[0] = hfe_sub(prev, evals[1]);                                                 // :188
         interpolate(evals, coeffs);                                                         // :189-192
         for (size_t i = 1; i <= td; i++) { hfe_store(coeffs_out + 16 * (k * td + i - 1), coeffs[i]); absorb_fe(t, coeffs[i]); }

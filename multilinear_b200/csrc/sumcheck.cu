@@ -174,6 +174,53 @@ __global__ void __launch_bounds__(SC_THREADS) wsumcheck_partial_kernel(const fe*
     fe s = block_sum(acc_reduce(a), scratch);
     if (threadIdx.x == 0) fe_store(partials + blockIdx.x, s);
 }
+// All evaluation points r = 1 .. TD of one round in a single pass over the tables (the reference makes one pass per point,
+// sumcheck.rs:185-187).  The interpolated row at integer r is x0 + r (x1 - x0), so consecutive points differ by the row
+// difference: row_1 = x1, row_{r+1} = row_r + (x1 - x0) — additions only, no interpolation multiplies; same for delta.
+template <int TD>
+__global__ void __launch_bounds__(SC_THREADS) wsumcheck_points_kernel(const fe* __restrict__ m, const fe* __restrict__ d, size_t off, int width,
+                                                                      WTerms terms, fe* __restrict__ partials) {
+    __shared__ fe scratch[32];
+    __shared__ fe t_coef[W_MAX_TERMS];
+    __shared__ uint32_t t_len[W_MAX_TERMS], t_off[W_MAX_TERMS], t_cols[W_MAX_COLS];
+    for (int t = threadIdx.x; t < terms.n_terms; t += blockDim.x) { t_coef[t] = terms.coef[t]; t_len[t] = terms.len[t]; t_off[t] = terms.off[t]; }
+    for (int c = threadIdx.x; c < terms.n_cols; c += blockDim.x) t_cols[c] = terms.cols[c];
+    __syncthreads();
+    fe_acc a[TD];
+#pragma unroll
+    for (int k = 0; k < TD; k++) acc_zero(a[k]);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < off; i += stride) {
+        fe row[W_MAX_WIDTH], diff[W_MAX_WIDTH];
+        for (int j = 0; j < width; j++) {
+            fe x0 = fe_load_nc(m + i * width + j), x1 = fe_load_nc(m + (i + off) * width + j);
+            row[j] = x1;
+            diff[j] = fe_sub(x1, x0);
+        }
+        fe d0 = fe_load_nc(d + i), dd = fe_load_nc(d + i + off);
+        const fe ddiff = fe_sub(dd, d0);
+#pragma unroll
+        for (int k = 0; k < TD; k++) {  // point r = k + 1
+            fe comp = fe_zero();
+            for (int t = 0; t < terms.n_terms; t++) {
+                fe p = t_coef[t];
+                for (uint32_t c = 0; c < t_len[t]; c++) p = fe_mul(p, row[t_cols[t_off[t] + c]]);
+                comp = fe_add(comp, p);
+            }
+            acc_mul_add(a[k], comp, dd);
+            if (k + 1 < TD) {
+                for (int j = 0; j < width; j++) row[j] = fe_add(row[j], diff[j]);
+                dd = fe_add(dd, ddiff);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < TD; k++) {
+        fe sk = block_sum(acc_reduce(a[k]), scratch);
+        if (threadIdx.x == 0) fe_store(partials + (size_t)TD * blockIdx.x + k, sk);
+    }
+}
 // fold (:234-247): rows i < off of the matrix and of delta, x <- x + r (x[i+off] - x)
 __global__ void __launch_bounds__(256) wsumcheck_fold_kernel(fe* __restrict__ m, fe* __restrict__ d, size_t off, int width, fe r) {
     size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -283,6 +330,28 @@ int wsumcheck_partial_sum_launch(const fe* m, const fe* d, size_t height, size_t
     reduce_partials_kernel<<<1, 256, 0, s>>>(partials, (int)nb, 1, partials + nb);
     MLB_KERNEL_CHECK();
     MLB_TRY(fetch(partials + nb, 1, out, s));
+    MLB_TRY(dev_free_async(partials, s));
+    return ML_OK;
+}
+// evals_out[k] = partial_sum(r = k + 1), k < td, in one pass; returns ML_ERR_ARG when td is outside the fused range
+int wsumcheck_points_launch(const fe* m, const fe* d, size_t height, size_t width, const fe* coef, const uint32_t* len, const uint32_t* off,
+                            const uint32_t* cols, size_t n_terms, size_t n_cols, int td, hfe* evals_out, cudaStream_t s) {
+    if (td < 1 || td > 4) return ML_ERR_ARG;
+    const size_t half = height >> 1;
+    const unsigned nb = blocks_for(half);
+    fe* partials;
+    MLB_TRY(dev_alloc_async((void**)&partials, ((size_t)nb + 1) * td * 16, s));
+    WTerms t{coef, len, off, cols, (int)n_terms, (int)n_cols};
+    switch (td) {
+        case 1: wsumcheck_points_kernel<1><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+        case 2: wsumcheck_points_kernel<2><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+        case 3: wsumcheck_points_kernel<3><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+        default: wsumcheck_points_kernel<4><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+    }
+    MLB_KERNEL_CHECK();
+    reduce_partials_kernel<<<1, 256, 0, s>>>(partials, (int)nb, td, partials + (size_t)nb * td);
+    MLB_KERNEL_CHECK();
+    MLB_TRY(fetch(partials + (size_t)nb * td, td, evals_out, s));
     MLB_TRY(dev_free_async(partials, s));
     return ML_OK;
 }

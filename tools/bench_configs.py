@@ -85,5 +85,26 @@ c_p = (time.perf_counter() - t0) * 1e3
 gp = ml.PCSProof.prove_dev(in1, out1, d1, n, ml.Transcript(), None)
 res["config1_pcs_prove_nvars20"] = {"gpu_ms": t_p, "cpu_ms": c_p, "bit_exact_vs_oracle": gp.fri_proof.serialize() == op.fri.blob,
                                     "verifies": gp.verify(ml.Transcript()) == 0}
+# ---- the reference's sumcheck_high_bench (src/constraint_system/sumcheck.rs:368-398): pythagorean trace, width 4, 2^20 rows
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
+from test_oracle import pythagorean_system
+M_ = 2**128 - 45 * 2**40 + 1
+def wide(log_h, use_gpu):
+    matrix, row_point, terms, t = pythagorean_system(O, log_h)
+    if use_gpu:
+        g = ml.WideSumcheckTables.build(row_point, matrix, 4); g.set_composition(terms)
+        tt = ml.Transcript()
+        f = lambda: None
+        t0 = time.perf_counter(); out = g.compute_sumcheck_polynomials(2, tt, 0); dt = time.perf_counter() - t0
+    else:
+        o = O.wsumcheck_build(row_point, matrix, 4); o.set_composition(terms)
+        t0 = time.perf_counter(); out = o.compute_sumcheck_polynomials(2, t, 0); dt = time.perf_counter() - t0
+    return dt * 1e3, out
+wide(12, True)  # warm-up
+g_ms, g_out = wide(20, True)
+c_ms, c_out = wide(16, False)
+g16_ms, g16_out = wide(16, True)
+res["sumcheck_high_bench_2p20_x4"] = {"gpu_ms_2p20_proof_only": g_ms, "gpu_ms_2p16": g16_ms, "cpu_ms_2p16_single_thread": c_ms,
+                                      "bit_exact_vs_oracle_2p16": g16_out == c_out}
 res["cpu_threads"] = os.cpu_count()
 print(json.dumps(res, indent=1))
