@@ -301,7 +301,7 @@ def run_ours(args):
         del pr
         L.ml_profile_reset()
         L.ml_profile_enable(1)
-        barrier()
+        torch.cuda.synchronize()  # rank-local leg: no cross-rank barrier inside the try block
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
         reps = 3
@@ -309,7 +309,7 @@ def run_ours(args):
             pr = ml.PCSProof.prove_dev(pts, claim, coeffs[0], n, ml.Transcript(), streams[0].value)
             del pr
         p1.record()
-        barrier()
+        torch.cuda.synchronize()  # rank-local leg: no cross-rank barrier inside the try block
         L.ml_profile_enable(0)
         pk = {}
         for i, name in enumerate(PROF_NAMES):
