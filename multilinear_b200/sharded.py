@@ -48,6 +48,13 @@ class CudaBackend:
             self._side = torch.cuda.Stream(device=self.device)
         return self._side
 
+    def encode_streams(self):
+        """two streams for the per-polynomial encodes: consecutive polynomials overlap, so the partial last wave of one NTT
+        pass (2^23 points = 4.6 waves of CTAs) is filled by the next polynomial's kernels"""
+        if getattr(self, "_enc2", None) is None:
+            self._enc2 = torch.cuda.Stream(device=self.device)
+        return [torch.cuda.current_stream(), self._enc2]
+
     def empty(self, nbytes):
         return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
 
@@ -162,9 +169,18 @@ def sharded_batch_commit(local_evals, n, n_polys, backend, dist=None, mode="seri
         mode = "pipelined"
     if mode == "serial":
         send = backend.empty(world * n_local * chunk)
-        for pl, ev in enumerate(local_evals):  # phase 1 + packing in exchange order
-            code = backend.encode(ev, n)
-            backend.pack_pairs(code, n_code, world, n_local, pl, send)
+        if getattr(backend, "is_cuda", False):
+            enc = backend.encode_streams()
+            enc[1].wait_stream(enc[0])
+            for pl, ev in enumerate(local_evals):  # phase 1 + packing in exchange order, alternating between two streams
+                with torch.cuda.stream(enc[pl & 1]):
+                    code = backend.encode(ev, n)
+                    backend.pack_pairs(code, n_code, world, n_local, pl, send)
+            enc[0].wait_stream(enc[1])
+        else:
+            for pl, ev in enumerate(local_evals):
+                code = backend.encode(ev, n)
+                backend.pack_pairs(code, n_code, world, n_local, pl, send)
         if world > 1:  # phase 2
             recv = backend.empty(world * n_local * chunk)
             dist.all_to_all_single(recv, send)
@@ -187,13 +203,16 @@ def sharded_batch_commit(local_evals, n, n_polys, backend, dist=None, mode="seri
     if mode == "p2p":
         codes = [backend.empty(32 * n) for _ in range(2)]
         freed = [None, None]  # event: the store pass has finished reading code buffer b
+        enc = backend.encode_streams()
+        enc[1].wait_stream(enc[0])
         for pl, ev in enumerate(local_evals):
             b = pl & 1
-            if freed[b] is not None:
-                main.wait_event(freed[b])
-            backend.encode(ev, n, out=codes[b])
-            done = torch.cuda.Event()
-            done.record(main)
+            with torch.cuda.stream(enc[b]):  # code buffer b belongs to encode stream b
+                if freed[b] is not None:
+                    enc[b].wait_event(freed[b])
+                backend.encode(ev, n, out=codes[b])
+                done = torch.cuda.Event()
+                done.record(enc[b])
             with torch.cuda.stream(side):  # NVLink stores overlap the next polynomial's NTT
                 side.wait_event(done)
                 backend.pack_pairs_peer(codes[b], n_code, world, pl * world + rank, bases, max_ctas=p2p_ctas)
@@ -209,18 +228,30 @@ def sharded_batch_commit(local_evals, n, n_polys, backend, dist=None, mode="seri
     recv = backend.empty(n_polys * chunk)
     sends = [backend.empty(world * chunk) for _ in range(2 if cuda else 1)]
     freed = [None, None]
+    enc = backend.encode_streams() if cuda else None
+    if cuda:
+        enc[1].wait_stream(enc[0])
     for pl, ev in enumerate(local_evals):
         b = pl & 1 if cuda else 0
-        if cuda and freed[b] is not None:
-            main.wait_event(freed[b])
-        code = backend.encode(ev, n)
-        backend.pack_pairs(code, n_code, world, 1, 0, sends[b])  # [dest][rows][32]
         dst = recv[pl * world * chunk:(pl + 1) * world * chunk]   # [src][rows][32] = polys pl*world .. pl*world+world-1
+        if cuda:
+            with torch.cuda.stream(enc[b]):  # send buffer b belongs to encode stream b
+                if freed[b] is not None:
+                    enc[b].wait_event(freed[b])
+                code = backend.encode(ev, n)
+                backend.pack_pairs(code, n_code, world, 1, 0, sends[b])  # [dest][rows][32]
+                if world == 1:
+                    dst.copy_(sends[b])
+                done = torch.cuda.Event()
+                done.record(enc[b])
+        else:
+            code = backend.encode(ev, n)
+            backend.pack_pairs(code, n_code, world, 1, 0, sends[b])
+            if world == 1:
+                dst.copy_(sends[b])
         if world == 1:
-            dst.copy_(sends[b])
+            pass
         elif cuda:
-            done = torch.cuda.Event()
-            done.record(main)
             with torch.cuda.stream(side):
                 side.wait_event(done)
                 dist.all_to_all_single(dst, sends[b])
@@ -228,7 +259,9 @@ def sharded_batch_commit(local_evals, n, n_polys, backend, dist=None, mode="seri
                 freed[b].record(side)
         else:
             dist.all_to_all_single(dst, sends[b])
-    if cuda and world > 1:
-        main.wait_stream(side)
+    if cuda:
+        main.wait_stream(enc[1])
+        if world > 1:
+            main.wait_stream(side)
     root = backend.leaf_subtree_root(recv, offsets, rows)
     return _finish(root, backend, dist, world)
