@@ -588,3 +588,28 @@ def test_c_example_pcs_prove(ml, golden):
     assert p.returncode == 0, p.stdout + p.stderr
     assert "root_0 623d135873c76f2306354b0d146b44c42c649d3060eaa022b0c0a96a4e051de2" in p.stdout   # SURVEY.md §8c PCS vector
     assert "accepted" in p.stdout
+
+
+def test_sharded_batch_commit_two_gpus_all_exchange_modes(ml):
+    """config 5 on two ranks over NCCL / NVLink peer stores (skipped on a one-GPU box): every exchange mode must give the
+    root of the single-GPU tree over all codes"""
+    import json
+    import os
+    import socket
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tools", "sharded_commit_demo.py"), "16", "8", "serial,pipelined,p2p"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{") and "batched_commit" in l]
+    assert [l["mode"] for l in lines] == ["serial", "pipelined", "p2p"]
+    assert all(l["matches_single_gpu"] is True and l["n_gpus"] == 2 for l in lines)
+    assert len({l["root"] for l in lines}) == 1
