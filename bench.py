@@ -88,8 +88,18 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def cpu_commit_rate(oracle_mod, log_n, threads, steps, warmup, seed=0xB200):
-    """Melem/s of the CPU oracle for reed_solomon + FriProverData::fold at 2^log_n coefficients"""
+def workload_config(args):
+    """the `config` object of the JSON line: a function of the command line only, identical for both arms"""
+    P = max(1, args.polys_per_gpu)
+    return {"workload": "pcs_commit_rs_merkle_fri_fold", "log_n": args.log_n, "blowup": 2, "polys_per_gpu": P,
+            "step": "one commit of each of the %d resident polynomials of 2^%d coefficients per GPU" % (P, args.log_n),
+            "l2": "inputs larger than L2 (256 MiB coefficients, 512 MiB code per commit)",
+            "parallelism": "independent commits: %d streams per GPU, no data-path collective" % P}
+
+
+def cpu_commit_rate(oracle_mod, log_n, threads, steps, warmup, seed=0xB200, keep=None):
+    """Melem/s of the CPU oracle for reed_solomon + FriProverData::fold at 2^log_n coefficients; keep (a dict) receives the
+    roots, last element and final transcript state of the last commit (the parity check of the bench line)"""
     from oracle.binding import fe_ints
     O = oracle_mod.Oracle(threads=threads)
     n = 1 << log_n
@@ -100,9 +110,12 @@ def cpu_commit_rate(oracle_mod, log_n, threads, steps, warmup, seed=0xB200):
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         code = O.reed_solomon(coeffs, gen)
-        f, st = O.fri_fold(gp, code, O.transcript())
+        tr = O.transcript()
+        f, st = O.fri_fold(gp, code, tr)
         dt = time.perf_counter() - t0
         assert st == 0 and f.last_element() is not None
+        if keep is not None:
+            keep.update(roots=f.roots(), last=f.last_element(), transcript=tr.random(), log_n=log_n, seed=seed)
         del f
         if it >= warmup:
             times.append(dt)
@@ -134,9 +147,10 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u128", "data": "synthetic",
-        "config": {"workload": "pcs_commit_rs_merkle_fri_fold", "log_n": args.log_n, "sample_log_n": log_n, "blowup": 2,
-                   "note": "CPU oracle = C restatement of the reference (Rust toolchain and winter-math/sha2 sources unavailable)"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(args),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "sample_log_n": log_n,
+                         "note": "CPU oracle = C restatement of the reference, OpenMP over all host threads (the Rust crate cannot be "
+                                 "built here: no cargo, no winter-math/sha2 sources); the reference itself is single-threaded"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -180,8 +194,16 @@ def run_batched_commit(torch, ml, L, dist, world, rank, n_polys, log_n, reps=3):
     be.release_peer_buffers()
     del mine
     torch.cuda.empty_cache()
+    fixture_ok = None
+    try:  # the oracle's root for exactly this workload (tests/golden/gen_batch_root.py)
+        fx = json.load(open(os.path.join(ROOT, "tests", "golden", "batch_root_64x2p22.json")))
+        if fx["n_polys"] == n_polys and fx["log_n"] == log_n:
+            fixture_ok = bool(fx["root"] == root.hex())
+    except Exception:  # noqa: BLE001
+        pass
     return {"workload": "batched_commit_%dx2^%d" % (n_polys, log_n), "mode": mode, "ms": ms, "value": n_polys * n / (ms * 1e-3) / 1e6,
-            "unit": UNIT, "scaling": "strong", "root": root.hex(), "launches_per_commit_per_rank": per_call,
+            "unit": UNIT, "scaling": "strong", "root": root.hex(), "root_matches_oracle_fixture": fixture_ok,
+            "launches_per_commit_per_rank": per_call,
             "exchange": "none" if world == 1 else "pack pass stores pairs into peer HBM over NVLink (CUDA IPC); barrier + 32-byte root all-gather over NCCL"}
 
 
@@ -217,8 +239,9 @@ def run_ours(args):
     results = [None] * P
 
     def commit(j):
-        f = ml.FriProverData.fold_from_coeffs_dev(coeffs[j], n, ml.Transcript(), streams[j].value)
-        out = (f.fold_roots(), f.last_element)
+        t = ml.Transcript()
+        f = ml.FriProverData.fold_from_coeffs_dev(coeffs[j], n, t, streams[j].value)
+        out = (f.fold_roots(), f.last_element, t.random())
         del f  # the handle (all layers, ~3.5 GB at 2^24) returns to the stream-ordered pool
         return out
 
@@ -258,7 +281,7 @@ def run_ours(args):
     sampler.stop_flag = True
     ms = e0.elapsed_time(e1) / args.steps
     launches = ml.kernel_launches() - launches0
-    roots, last = results[0]
+    roots, last, tr0 = results[0]
 
     # ---- serial pass of the same workload (one commit at a time) with per-kernel CUDA-event timing: per-kernel
     # durations are only well defined when commits do not share the GPU
@@ -455,21 +478,32 @@ def run_ours(args):
             extra["int_pipe_error"] = str(e)
 
         cpu_baseline = None
+        parity_at_size, parity_detail = None, None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import binding
             binding.build()
             threads = os.cpu_count() or 1
             log_s = pick_cpu_sample(binding, threads, 2, 25.0)
-            rate, mean = cpu_commit_rate(binding, log_s, threads, 1, 1)
+            kept = {}
+            rate, mean = cpu_commit_rate(binding, log_s, threads, 1, 1, keep=kept)
             cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": "reed_solomon + FriProverData::fold at 2^%d coefficients, %.2f s per commit, all host threads (OpenMP)" % (log_s, mean)}
+            # parity at size: the oracle's commit of the same polynomial (seed 0xB200 = this rank's polynomial 0) against the
+            # CUDA path's: every layer root, the last element and the final transcript state
+            if log_s == args.log_n:
+                g_roots, g_last, g_tr = roots, last, tr0
+            else:  # the CPU sample had to be smaller than the workload: commit that size on the GPU too
+                tt = ml.Transcript()
+                ff = ml.FriProverData.fold_from_coeffs_dev(ml.synthetic_elements_dev(0xB200, 1 << log_s), 1 << log_s, tt, streams[0].value)
+                g_roots, g_last, g_tr = ff.fold_roots(), ff.last_element, tt.random()
+                del ff
+            parity_at_size = bool(g_roots == kept["roots"] and g_last == kept["last"] and g_tr == kept["transcript"])
+            parity_detail = {"log_n": log_s, "seed": "0xB200", "roots_compared": len(kept["roots"]), "last_element": g_last == kept["last"],
+                             "transcript": g_tr == kept["transcript"], "checker": "oracle/oracle.c (CPU restatement; unpinned against the Rust crate)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u128", "data": "synthetic",
-            "config": {"workload": "pcs_commit_rs_merkle_fri_fold", "log_n": args.log_n, "blowup": 2, "polys_per_gpu": P,
-                       "step": "one commit of each of the %d resident polynomials of 2^%d coefficients per GPU" % (P, args.log_n),
-                       "l2": "inputs larger than L2 (256 MiB coefficients, 512 MiB code per commit)",
-                       "parallelism": "independent commits: %d streams per GPU, no data-path collective" % P},
+            "config": workload_config(args),
             "serial": {"ms_per_commit": ms_serial, "value": world * n / (ms_serial * 1e-3) / 1e6, "unit": UNIT,
                        "note": "one commit at a time on one stream (latency-bound phases exposed)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
@@ -480,14 +514,20 @@ def run_ours(args):
                     "proof_readout_ms_mean": 1e3 * sum(p[1] for p in e2e_phase) / (PE * e2e_steps)},
             "gpu_launches": launches, "clocks": sampler.result(), "kernels": kernels,
         }
-        if batched is not None:
-            line["batched_commit"] = batched
+        if parity_at_size is not None:
+            if roofline is not None:  # driver-preserved key (config must stay identical to the reference arm's)
+                roofline["parity_at_size"] = parity_at_size
+            if line["cpu_baseline"] is not None:
+                line["cpu_baseline"]["parity_at_size"] = parity_at_size
+            line["parity"] = parity_detail
         if pcs_prove is not None:
             if "hbm_bound_kernels" in pcs_prove:
                 for v in pcs_prove["hbm_bound_kernels"].values():
                     v["frac_of_hbm_peak"] = v["achieved_gbs"] / hbm_peak if v["achieved_gbs"] else None
             line["pcs_prove"] = pcs_prove
         line.update(extra)
+        if batched is not None:  # last key: the driver keeps the tail of the line
+            line["batched_commit"] = batched
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

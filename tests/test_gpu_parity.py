@@ -496,7 +496,124 @@ def test_sharded_batch_commit_single_gpu(ml, oracle, mode):
     assert root == oracle.merkle_batch_commit(datas).root()
 
 
-# ------------------------------------------------------------------ full-size properties (BASELINE sizes; oracle too slow here)
+# ------------------------------------------------------------------ oracle parity AT the BASELINE sizes (configs 2-5)
+# The oracle needs seconds per case on the box's host cores (all threads); every comparison is bit-exact.
+@pytest.fixture(scope="module")
+def big_oracle():
+    import os
+    from oracle import binding
+    binding.build()
+    return binding.Oracle(threads=os.cpu_count() or 1)
+
+
+def test_atsize_config3_commit_2p24_roots_last_transcript(ml, big_oracle):
+    """BASELINE configs[2]: reed_solomon + FriProverData::fold of 2^24 coefficients (seed 0xB200, bench.py's polynomial 0):
+    all 24 layer roots, the last element and the final transcript state equal the oracle's (src/fri/mod.rs:136-145)"""
+    O = big_oracle
+    n = 1 << 24
+    coeffs = O.synthetic(0xB200, n)
+    gp = O.pow2_generator_powers(25)
+    code = O.reed_solomon(coeffs, fe_ints(gp[1:2])[0])
+    ot = O.transcript()
+    of, st = O.fri_fold(gp, code, ot)
+    assert st == 0
+    dev = ml.synthetic_elements_dev(0xB200, n)
+    t = ml.Transcript()
+    f = ml.FriProverData.fold_from_coeffs_dev(dev, n, t)
+    roots = f.fold_roots()
+    assert len(roots) == 24 and roots == of.roots()
+    assert f.last_element == of.last_element() and f.last_element is not None
+    assert t.random() == ot.random()
+    # the code itself (2^25 evaluations, the (9, 8, 8) pass plan) equals the oracle's, element for element
+    assert np.array_equal(ml.reed_solomon(coeffs, ml.pow_2_generator(25)), code)
+
+
+def test_atsize_config2_ntt_2p20_blowup2_forward_inverse(ml, big_oracle):
+    """BASELINE configs[1]: standalone forward + inverse NTT, one polynomial of 2^20 coefficients with blowup 2"""
+    O = big_oracle
+    n = 1 << 20
+    c = O.synthetic(0xB200, n)
+    g = ml.pow_2_generator(21)
+    code = ml.reed_solomon(c, g)
+    want = O.reed_solomon(c, g)
+    assert np.array_equal(code, want)
+    back = ml.intt(code, g)
+    assert np.array_equal(back, O.intt(want, g))
+    assert np.array_equal(back[:n], c) and not back[n:].any()
+
+
+def test_atsize_config4_sumcheck_2p24_all_rounds(ml, big_oracle):
+    """BASELINE configs[3]: sumcheck over a 2^24-entry multilinear extension product f * eq (composition x[0]), all 24 rounds:
+    every (c1, c2), every challenge and the transcript equal the oracle's (sumcheck.rs:147-202)"""
+    O = big_oracle
+    nv = 24
+    ev = O.synthetic(0xB200, 1 << nv)
+    inp = O.synthetic(0xB2000001, nv)
+    claim = O.mle_evals_evaluate(ev, inp)
+    assert ml.MultilinearPolynomialEvals(ev).evaluate(ml.to_ints(inp)) == claim
+    t, ot = ml.Transcript(), O.transcript()
+    s, os_ = ml.SumcheckTables.build_tables_for_pcs(inp, ev), O.sumcheck_build(inp, ev)
+    got = s.compute_sumcheck_polynomials(1, t, claim)
+    want = os_.compute_sumcheck_polynomials(1, ot, claim)
+    assert len(got[0]) == 2 * nv and got == want
+    assert t.random() == ot.random()
+
+
+def test_atsize_pcs_prove_n_vars_24(ml, big_oracle):
+    """PCSProof::prove at the metric's size (n_vars = 24): proof bytes, sumcheck polynomials and transcript equal the oracle's"""
+    O = big_oracle
+    nv = 24
+    ev = O.synthetic(0xB200, 1 << nv)
+    inp = O.synthetic(0xB2000001, nv)
+    out = O.mle_evals_evaluate(ev, inp)
+    t, ot = ml.Transcript(), O.transcript()
+    proof = ml.PCSProof.prove(inp, out, ev, t)
+    oproof, st = O.pcs_prove(inp, out, ev, ot)
+    assert st == 0 and hashlib.sha256(proof.fri_proof.serialize()).digest() == hashlib.sha256(oproof.fri.blob).digest()
+    assert [c for nz in proof.sumcheck_polynomials for c in nz] == oproof.sumcheck and t.random() == ot.random()
+    assert proof.verify(ml.Transcript()) == 0
+
+
+def oracle_batch_root_by_ranges(O, seeds, n, n_ranges=8):
+    """Merkle::batch_commit root over the RS codes of polys synthetic(seed, n), computed range by range to bound memory:
+    the tree over all leaves equals the tree over the roots of equal leaf ranges (merkle_tree/mod.rs:118-129)"""
+    g = O.pow2_generator((n.bit_length() - 1) + 1)
+    codes = [O.reed_solomon(O.bit_reverse(O.to_coefficient(O.synthetic(s, n))), g) for s in seeds]
+    rows = n // n_ranges
+    roots = []
+    for r in range(n_ranges):
+        datas = [np.concatenate([c[r * rows:(r + 1) * rows], c[n + r * rows:n + (r + 1) * rows]], axis=1) for c in codes]
+        roots.append(O.merkle_batch_commit(datas).root())
+    while len(roots) > 1:
+        roots = [hashlib.sha256(roots[i] + roots[i + 1]).digest() for i in range(0, len(roots), 2)]
+    return roots[0]
+
+
+def test_atsize_config5_batch_root_64x2p22(ml, big_oracle):
+    """BASELINE configs[4]: batch root of 64 polynomials of 2^22 evaluations (bench.py's seeds 5000 + j) equals the oracle's
+    Merkle::batch_commit over the 64 RS codes; the committed fixture (tests/golden/gen_batch_root.py) must agree with both"""
+    import json
+    import os
+    import torch
+    from multilinear_b200.sharded import CudaBackend, sharded_batch_commit
+    n, B = 1 << 22, 64
+    want = oracle_batch_root_by_ranges(big_oracle, [5000 + j for j in range(B)], n)
+    import ctypes as C
+    from multilinear_b200 import load
+    L = load()
+    local = []
+    for j in range(B):
+        t = torch.empty(16 * n, dtype=torch.uint8, device="cuda")
+        ml.check(L.ml_synthetic_elements_dev(C.c_uint64(5000 + j), C.c_size_t(n), C.c_void_p(t.data_ptr()),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        local.append(t)
+    root = sharded_batch_commit(local, n, B, CudaBackend(), None, mode="serial")
+    assert root == want
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "batch_root_64x2p22.json")))
+    assert fx["root"] == want.hex() and fx["n_polys"] == B and fx["log_n"] == 22
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE sizes; size-independent checks)
 def test_fullsize_ntt_roundtrip_and_linearity_2p24(ml):
     n = 1 << 24
     a = ml.synthetic_elements_dev(11, n).elems()
