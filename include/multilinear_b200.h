@@ -73,6 +73,17 @@ int ml_stream_destroy(void *stream);
 int ml_stream_synchronize(void *stream);
 int ml_set_thread_stream(void *stream, int enable);
 
+/* Device memory the library caches.  Scratch and handle-owned buffers are stream-ordered allocations: streams made by
+ * ml_stream_create get a private cudaMemPool (destroyed by ml_stream_destroy); any other stream (caller-owned, e.g. a
+ * framework's stream) allocates from the device's default pool.  Freed blocks stay cached for reuse — invisible to other allocators in the
+ * process — until released: ml_trim_pools returns cached blocks of the current device down to keep_bytes per pool,
+ * ml_release_pools synchronises the device and returns all of them, ml_set_pool_release_threshold bounds what stays cached at
+ * every synchronisation point (default: unbounded).  ml_pool_stats: bytes reserved from the driver / in use, current device. */
+int ml_trim_pools(size_t keep_bytes);
+int ml_release_pools(void);
+int ml_set_pool_release_threshold(uint64_t bytes);
+int ml_pool_stats(uint64_t *reserved_bytes, uint64_t *used_bytes);
+
 /* raw device memory for callers that keep data resident (bench, multi-GPU orchestration) */
 int ml_dev_alloc(size_t bytes, void **out);
 int ml_dev_free(void *p);
@@ -93,7 +104,10 @@ int ml_fe_from_i64_vec(const int64_t *v, size_t n, uint8_t *out);               
 int ml_fe_from_wide_vec(const uint8_t *v, size_t n, int variant, uint8_t *out);
 int ml_synthetic_elements_dev(uint64_t seed, size_t n, void *out_dev, void *stream); /* bench input generator */
 
-/* ---- NTT (src/ntt/mod.rs) ---- */
+/* ---- NTT (src/ntt/mod.rs) ----
+ * RESTRICTION (differs from the reference's generic signatures): `gen` must be the root the reference's own callers pass,
+ * pow_2_generator(log2 n) (n = the transform length; 2n for reed_solomon), or its inverse; anything else returns
+ * ML_ERR_GENERATOR instead of computing with it.  The kernels take their twiddles from per-size root tables kept in HBM. */
 int ml_pow2_generator(uint64_t log_size, uint8_t out[16]);            /* NttField::pow_2_generator :42-54 */
 int ml_pow2_generator_powers(uint64_t log_size, uint8_t *out);        /* pow_2_generator_powers :18-28 (2^log_size elements) */
 int ml_pow2_generator_powers_dev(uint64_t log_size, void *out_dev, void *stream);
@@ -147,8 +161,11 @@ typedef struct ml_fri ml_fri;             /* FriProverData :10-14 — all trees 
 typedef struct ml_fri_proof ml_fri_proof; /* FriProof :239-249 */
 int ml_fri_init(const uint8_t *code, size_t n, ml_transcript *t, ml_fri **out);                      /* init :58-76 */
 int ml_fri_init_dev(const void *code_dev, size_t n, ml_transcript *t, void *stream, ml_fri **out);   /* code is copied */
-/* fold_step :79-134.  gen_pows may be NULL (the backend keeps its own root tables in HBM); when given,
- * gen_pows_len must equal the original domain size and gen_pows[1] the domain generator. */
+/* fold_step :79-134.  gen_pows may be NULL (the backend keeps its own root tables in HBM).  RESTRICTION: when given it must be
+ * pow_2_generator_powers(log2 domain) — length = original domain size, entries spot-checked (21 positions) against the
+ * domain generator's powers, ML_ERR_SIZE / ML_ERR_GENERATOR otherwise; the kernels never read the caller's table.
+ * Host-pointer entry points block the calling thread: inputs of 16 MB and more are uploaded one at a time per device
+ * (after the calling thread's stream has drained) and results are read back before returning. */
 int ml_fri_fold_step(ml_fri *f, const uint8_t *gen_pows, size_t gen_pows_len, size_t k, const uint8_t r[16], ml_transcript *t);
 int ml_fri_fold(const uint8_t *gen_pows, size_t gen_pows_len, const uint8_t *code, size_t n, ml_transcript *t, ml_fri **out); /* fold :136-145 */
 int ml_fri_fold_dev(const void *code_dev, size_t n, ml_transcript *t, void *stream, ml_fri **out);
@@ -276,21 +293,6 @@ int ml_ipc_alloc(size_t bytes, void **dev_out, uint8_t handle_out[64]);
 int ml_ipc_open(const uint8_t handle[64], void **dev_out);
 int ml_ipc_close(void *dev);
 int ml_ipc_free(void *dev);
-
-/* host-side phase trace of the host-pointer prove path (recorded when MLB_TRACE is set in the environment); prints to stderr */
-void ml_trace_dump(void);
-
-/* ---- instrumentation for bench.py ----
- * ml_profile_*: when enabled, every kernel group is bracketed by CUDA events on its launch stream;
- * ml_profile_get sums device time, launches and algorithmic HBM bytes (input read once + output written once)
- * per group id: 0 ntt_pass, 1 merkle_leaf_subtree, 2 merkle_nodes, 3 merkle_top, 4 fri_fold, 5 sumcheck_sums,
- * 6 sumcheck_fold, 7 mobius, 8 eq_table, 9 bit_reverse, 10 query_gather, 11 fused_tail, 12 transcript_step.
- * ml_microbench: integer-pipe speed-of-light loops ("modmul", "butterfly", "sha_leaf", "sha_node", "copy"). */
-int ml_profile_enable(int on);
-int ml_profile_reset(void);
-int ml_profile_get(int id, double *total_ms, uint64_t *launches, double *alg_bytes);
-int ml_profile_get_max(int id, double *mean_ms, uint64_t *launches, double *alg_bytes); /* the group's largest launches */
-int ml_microbench(const char *what, size_t n, int iters, double *ms_out, double *work_out);
 
 #ifdef __cplusplus
 }

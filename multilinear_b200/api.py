@@ -694,7 +694,16 @@ class BatchedPCSProof:
         return PCSProof(h, batched=True)
 
 
+_INSTR = None
+
+
 def microbench(what, n, iters):
+    """integer-pipe speed-of-light loops (instrumentation library libmlb_instr.so, include/multilinear_b200_instr.h)"""
+    global _INSTR
+    if _INSTR is None:
+        import os
+        load()  # the instrumentation library links against the product library
+        _INSTR = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmlb_instr.so"))
     ms, work = C.c_double(0), C.c_double(0)
-    check(load().ml_microbench(what.encode(), _sz(n), C.c_int(iters), C.byref(ms), C.byref(work)))
+    check(_INSTR.ml_microbench(what.encode(), _sz(n), C.c_int(iters), C.byref(ms), C.byref(work)))
     return ms.value, work.value

@@ -7,8 +7,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmultilinear_b200.so")
-SOURCES = ["core.cu", "field_ops.cu", "ntt.cu", "merkle.cu", "fri.cu", "sumcheck.cu", "mle.cu", "prover.cu", "chain.cu", "microbench.cu"]
-HEADERS = ["field.cuh", "sha256.cuh", "reduce.cuh", "transcript.cuh", "internal.h", "handles.h", os.path.join("..", "..", "include", "multilinear_b200.h")]
+SOURCES = ["core.cu", "field_ops.cu", "ntt.cu", "merkle.cu", "fri.cu", "sumcheck.cu", "mle.cu", "prover.cu", "chain.cu"]
+# instrumentation (integer-pipe speed-of-light loops for bench.py / tools): its own library, not part of the product ABI
+INSTR_OUT = os.path.join(HERE, "libmlb_instr.so")
+INSTR_SOURCES = ["microbench.cu"]
+HEADERS = ["field.cuh", "sha256.cuh", "reduce.cuh", "transcript.cuh", "internal.h", "handles.h", os.path.join("..", "..", "include", "multilinear_b200.h"),
+           os.path.join("..", "..", "include", "multilinear_b200_instr.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC", "-diag-suppress", "177",
@@ -23,10 +27,10 @@ def _nvcc():
 
 
 def needs_build():
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(INSTR_OUT):
         return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    t = min(os.path.getmtime(OUT), os.path.getmtime(INSTR_OUT))
+    deps = [os.path.join(CSRC, f) for f in SOURCES + INSTR_SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
@@ -38,20 +42,23 @@ def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
-    for src in SOURCES:
+    for src in SOURCES + INSTR_SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
-    objs = []
+    objs, instr_objs = [], []
     for src, obj, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:
             sys.stderr.write(out.decode(errors="replace"))
             raise RuntimeError("nvcc failed on %s" % src)
-        objs.append(obj)
+        (instr_objs if src in INSTR_SOURCES else objs).append(obj)
     cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    subprocess.check_call(cmd)
+    cmd = [nvcc, "-shared", "-o", INSTR_OUT] + instr_objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-L", HERE,
+           "-lmultilinear_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
     subprocess.check_call(cmd)
     return OUT
 

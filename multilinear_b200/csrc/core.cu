@@ -51,6 +51,7 @@ cudaStream_t lib_stream(Ctx* ctx) { return tl_stream_set ? tl_stream : ctx->stre
 
 static std::mutex g_ctx_mu;
 static std::map<int, Ctx*> g_ctx;
+static unsigned long long g_release_threshold_init();
 
 int get_ctx(Ctx** out) {
     int dev = 0;
@@ -70,7 +71,7 @@ int get_ctx(Ctx** out) {
         MLB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         cudaMemPool_t pool;
         MLB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-        unsigned long long thr = ~0ull;  // keep freed scratch cached in the pool
+        unsigned long long thr = g_release_threshold_init();  // keep freed scratch cached in the pool (ml_set_pool_release_threshold bounds it)
         MLB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
         // default pool (only used for the legacy stream now, see pool_for): never satisfy an allocation on one stream with a
         // block whose free is still queued on another stream — the driver does that by making the allocating stream wait
@@ -82,37 +83,50 @@ int get_ctx(Ctx** out) {
     *out = it->second;
     return ML_OK;
 }
-// One memory pool per (device, stream).  Concurrent commits run on their own streams and make ~100 stream-ordered allocations
-// each, up to 512 MB.  In the shared default pool a block freed on stream A and requested on stream B either makes B wait for
-// A's pending work (internal dependencies) or forces the pool to grow with slow virtual-memory calls under a driver-wide lock;
-// both showed up as erratic end-to-end times (75 ms to > 1 s per step with 8 commits in flight, tools/e2e_probe.py traces: every
-// thread stuck in cudaMallocAsync / kernel launches at once).  With a private pool per stream every block is recycled on the
-// stream that freed it: no cross-stream waits, and no growth after the first commit.
+// One memory pool per (device, LIBRARY-OWNED stream).  Concurrent commits run on their own streams and make ~100 stream-ordered
+// allocations each, up to 512 MB.  In the shared default pool a block freed on stream A and requested on stream B either makes B
+// wait for A's pending work (internal dependencies) or forces the pool to grow with slow virtual-memory calls under a driver-wide
+// lock; both showed up as erratic end-to-end times (75 ms to > 1 s per step with 8 commits in flight, tools/e2e_probe.py traces).
+// With a private pool per stream every block is recycled on the stream that freed it: no cross-stream waits, no growth after the
+// first commit.  Only streams made by ml_stream_create get a private pool (it dies with ml_stream_destroy); streams the caller owns
+// (torch streams, the legacy stream) allocate from the device's default pool, so the library never keeps memory keyed to a handle
+// whose lifetime it does not control.  Cached blocks are returned to the driver by ml_trim_pools / ml_release_pools, and the amount
+// a pool may keep cached is bounded by ml_set_pool_release_threshold (default: keep everything, the point of the pool).
 static std::mutex g_pool_mu;
-static std::map<std::pair<int, cudaStream_t>, cudaMemPool_t> g_pools;
-static cudaMemPool_t pool_for(cudaStream_t s) {
+static std::map<std::pair<int, cudaStream_t>, cudaMemPool_t> g_pools;  // library streams only; nullptr = creation failed, use default
+static std::atomic<unsigned long long> g_release_threshold{~0ull};
+static void register_stream_pool(int dev, cudaStream_t s) {
     static const bool shared = getenv("MLB_SHARED_POOL") != nullptr;
-    if (shared || s == nullptr) return nullptr;
+    cudaMemPool_t pool = nullptr;
+    if (!shared) {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaError_t e = cudaMemPoolCreate(&pool, &props);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            pool = nullptr;
+            fprintf(stderr, "multilinear_b200: cudaMemPoolCreate failed (%s); stream %p allocates from the device default pool\n",
+                    cudaGetErrorString(e), (void*)s);
+        } else {
+            unsigned long long thr = g_release_threshold.load();
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    g_pools[std::make_pair(dev, s)] = pool;
+}
+static unsigned long long g_release_threshold_init() { return g_release_threshold.load(); }
+static cudaMemPool_t pool_for(cudaStream_t s) {
+    if (s == nullptr) return nullptr;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
     std::lock_guard<std::mutex> lock(g_pool_mu);
-    auto key = std::make_pair(dev, s);
-    auto it = g_pools.find(key);
-    if (it != g_pools.end()) return it->second;
-    cudaMemPoolProps props;
-    memset(&props, 0, sizeof props);
-    props.allocType = cudaMemAllocationTypePinned;
-    props.handleTypes = cudaMemHandleTypeNone;
-    props.location.type = cudaMemLocationTypeDevice;
-    props.location.id = dev;
-    cudaMemPool_t pool = nullptr;
-    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); pool = nullptr; }
-    if (pool) {
-        unsigned long long thr = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-    g_pools.emplace(key, pool);
-    return pool;
+    auto it = g_pools.find(std::make_pair(dev, s));
+    return it == g_pools.end() ? nullptr : it->second;  // not a library stream: default pool
 }
 int dev_alloc_async(void** p, size_t bytes, cudaStream_t s) {
     if (bytes == 0) bytes = 16;
@@ -201,9 +215,61 @@ int ml_profile_get_max(int id, double* mean_ms, uint64_t* launches, double* alg_
     return ML_OK;
 }
 int ml_stream_create(void** out) {
+    Ctx* ctx;
+    MLB_TRY(get_ctx(&ctx));  // sets the default pool's attributes before the first allocation on this device
     cudaStream_t s;
     MLB_CUDA(cudaStreamCreate(&s));  // blocking stream: ordered against the legacy default stream (event timing in bench.py)
+    register_stream_pool(ctx->device, s);
     *out = (void*)s;
+    return ML_OK;
+}
+// cached (free) blocks of every pool the library allocates from on the current device go back to the driver, down to
+// `keep_bytes` per pool; blocks in use are untouched.  Call between phases when another allocator (e.g. PyTorch's) needs the HBM.
+int ml_trim_pools(size_t keep_bytes) {
+    int dev = 0;
+    MLB_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t def = nullptr;
+    MLB_CUDA(cudaDeviceGetDefaultMemPool(&def, dev));
+    MLB_CUDA(cudaMemPoolTrimTo(def, keep_bytes));
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (auto& kv : g_pools)
+        if (kv.first.first == dev && kv.second) MLB_CUDA(cudaMemPoolTrimTo(kv.second, keep_bytes));
+    return ML_OK;
+}
+int ml_release_pools(void) {
+    MLB_CUDA(cudaDeviceSynchronize());
+    return ml_trim_pools(0);
+}
+// upper bound on what a pool keeps cached after a free reaches a synchronisation point (cudaMemPoolAttrReleaseThreshold);
+// applies to existing pools of the current device and to every pool created later.  ~0 (default) keeps everything.
+int ml_set_pool_release_threshold(uint64_t bytes) {
+    g_release_threshold.store(bytes);
+    int dev = 0;
+    MLB_CUDA(cudaGetDevice(&dev));
+    unsigned long long thr = bytes;
+    cudaMemPool_t def = nullptr;
+    MLB_CUDA(cudaDeviceGetDefaultMemPool(&def, dev));
+    MLB_CUDA(cudaMemPoolSetAttribute(def, cudaMemPoolAttrReleaseThreshold, &thr));
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (auto& kv : g_pools)
+        if (kv.first.first == dev && kv.second) MLB_CUDA(cudaMemPoolSetAttribute(kv.second, cudaMemPoolAttrReleaseThreshold, &thr));
+    return ML_OK;
+}
+int ml_pool_stats(uint64_t* reserved_bytes, uint64_t* used_bytes) {
+    int dev = 0;
+    MLB_CUDA(cudaGetDevice(&dev));
+    unsigned long long res = 0, used = 0, v = 0;
+    cudaMemPool_t def = nullptr;
+    MLB_CUDA(cudaDeviceGetDefaultMemPool(&def, dev));
+    MLB_CUDA(cudaMemPoolGetAttribute(def, cudaMemPoolAttrReservedMemCurrent, &v)); res += v;
+    MLB_CUDA(cudaMemPoolGetAttribute(def, cudaMemPoolAttrUsedMemCurrent, &v)); used += v;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (auto& kv : g_pools) {
+        if (kv.first.first != dev || !kv.second) continue;
+        MLB_CUDA(cudaMemPoolGetAttribute(kv.second, cudaMemPoolAttrReservedMemCurrent, &v)); res += v;
+        MLB_CUDA(cudaMemPoolGetAttribute(kv.second, cudaMemPoolAttrUsedMemCurrent, &v)); used += v;
+    }
+    *reserved_bytes = res; *used_bytes = used;
     return ML_OK;
 }
 int ml_stream_destroy(void* stream) {

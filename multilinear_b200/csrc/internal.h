@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/multilinear_b200.h"
+#include "../../include/multilinear_b200_instr.h"
 
 namespace mlb {
 

@@ -269,9 +269,13 @@ int get_root_tables(Ctx* ctx, int log_n, cudaStream_t s, const RootTables** out)
         const size_t n = (size_t)1 << log_n;
         const unsigned n_lo = (unsigned)(n < ((size_t)1 << LO_BITS) ? n : ((size_t)1 << LO_BITS));
         const unsigned n_hi = (unsigned)(n >> LO_BITS ? n >> LO_BITS : 1);
-        MLB_CUDA(cudaMalloc((void**)&rt.lo, (size_t)n_lo * 16));
-        MLB_CUDA(cudaMalloc((void**)&rt.lo_ninv, (size_t)n_lo * 16));
-        MLB_CUDA(cudaMalloc((void**)&rt.hi, (size_t)n_hi * 16));
+        if (cudaMalloc((void**)&rt.lo, (size_t)n_lo * 16) != cudaSuccess || cudaMalloc((void**)&rt.lo_ninv, (size_t)n_lo * 16) != cudaSuccess ||
+            cudaMalloc((void**)&rt.hi, (size_t)n_hi * 16) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(rt.lo); cudaFree(rt.lo_ninv); cudaFree(rt.hi);  // cudaFree(nullptr) is a no-op
+            set_error("root tables for 2^%d: device allocation failed", log_n);
+            return ML_ERR_ALLOC;
+        }
         hfe gen_hi = hfe_pow(rt.gen, (hfe)1 << LO_BITS);
         hfe ninv = hfe_inv(hfe_new((hfe)n));
         unsigned m = n_lo > n_hi ? n_lo : n_hi;
@@ -336,8 +340,14 @@ int ntt_launch(Ctx* ctx, const fe* in, fe* out, int log_n, bool inverse, bool rs
     for (int p = 0; p < n_passes; p++) radix_log[p] = log_n / n_passes + (p < log_n % n_passes ? 1 : 0);
 
     // passes 0..P-2 are tile-in-place and run in a scratch buffer; the last pass scatters to natural order in `out`
-    fe* tmp = nullptr;
-    if (n_passes > 1) MLB_TRY(dev_alloc_async((void**)&tmp, ((size_t)16) << log_n, s));
+    struct TmpGuard {  // stream-ordered scratch released on every exit path
+        fe* p = nullptr;
+        cudaStream_t s;
+        explicit TmpGuard(cudaStream_t st) : s(st) {}
+        ~TmpGuard() { if (p) cudaFreeAsync(p, s); }
+    } tmp_guard(s);
+    if (n_passes > 1) MLB_TRY(dev_alloc_async((void**)&tmp_guard.p, ((size_t)16) << log_n, s));
+    fe* const tmp = tmp_guard.p;
 
     const double nbytes = 16.0 * (double)((size_t)1 << log_n);
     ProfScope prof(PROF_NTT_PASS, rs_zero_padded ? 1.5 * nbytes : 2.0 * nbytes, s);  // read input once + write output once
@@ -374,7 +384,6 @@ int ntt_launch(Ctx* ctx, const fe* in, fe* out, int log_n, bool inverse, bool rs
         MLB_KERNEL_CHECK();
         log_a += a.log_r;
     }
-    if (tmp) MLB_TRY(dev_free_async(tmp, s));
     return ML_OK;
 }
 

@@ -55,23 +55,30 @@ static void trace_dump_impl() {
     g_trace.clear();
 }
 static int stream_wait_blocking(cudaStream_t s);
-// Host -> device upload.  Large uploads from concurrent callers are serialised (one at a time, each waited for under the
-// lock): a copy engine shared by n uploads finishes all of them late, so n commits submitted together would all start their
-// NTT after the LAST byte of the LAST input arrived and then run in lock-step — copy phase with idle SMs, compute phase with an
-// idle copy engine (measured with 8 host-pointer commits in flight: 113-136 ms per step in lock-step, 75 ms when staggered).
+// Host -> device upload.  Large uploads from concurrent callers to ONE device are serialised (one at a time, each waited for
+// under that device's lock): a copy engine shared by n uploads finishes all of them late, so n commits submitted together would all
+// start their NTT after the LAST byte of the LAST input arrived and then run in lock-step — copy phase with idle SMs, compute phase
+// with an idle copy engine (measured with 8 host-pointer commits in flight: 113-136 ms per step in lock-step, 75 ms when staggered).
 // One upload at a time makes the stagger structural: commit k computes while commit k+1 uploads.
-static std::mutex g_upload_mu;
+// The caller's own earlier work on `s` is drained BEFORE the lock is taken, so under the lock only the copy itself is waited for and
+// a caller with kernels queued delays nobody but itself.  Host-pointer entry points are therefore host-synchronous for inputs of
+// 16 MB and more (documented in include/multilinear_b200.h).
+static const int MAX_UPLOAD_DEVICES = 64;
+static std::mutex g_upload_mu[MAX_UPLOAD_DEVICES];
 int h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
     if (!bytes) return ML_OK;
     if (bytes < ((size_t)16 << 20)) {
         MLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
         return ML_OK;
     }
+    int dev = 0;
+    MLB_CUDA(cudaGetDevice(&dev));
+    MLB_TRY(stream_wait_blocking(s));  // not under the lock: this stream's earlier work is this caller's own business
     trace("upload_wait");
-    std::lock_guard<std::mutex> lock(g_upload_mu);
+    std::lock_guard<std::mutex> lock(g_upload_mu[dev % MAX_UPLOAD_DEVICES]);
     trace("upload_begin");
     MLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
-    int st = stream_wait_blocking(s);
+    int st = stream_wait_blocking(s);  // the stream holds nothing but the copy now
     trace("upload_done");
     return st;
 }
@@ -1012,7 +1019,8 @@ int ml_fri_init_dev(const void* code_dev, size_t n, ml_transcript* t, void* stre
     cudaStream_t s = ST(stream);
     fe* code;
     MLB_TRY(pmalloc((void**)&code, n * 16, s));
-    MLB_CUDA(cudaMemcpyAsync(code, code_dev, n * 16, cudaMemcpyDeviceToDevice, s));
+    cudaError_t e = cudaMemcpyAsync(code, code_dev, n * 16, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) { pfree(code, s); set_error("copy failed: %s", cudaGetErrorString(e)); return ML_ERR_CUDA; }
     return fri_init_owned(out, code, n, true, t, s);
 }
 int ml_fri_init(const uint8_t* code_host, size_t n, ml_transcript* t, ml_fri** out) {
@@ -1021,15 +1029,28 @@ int ml_fri_init(const uint8_t* code_host, size_t n, ml_transcript* t, ml_fri** o
     cudaStream_t s = lib_stream(ctx);
     fe* code;
     MLB_TRY(pmalloc((void**)&code, n * 16, s));
-    MLB_CUDA(cudaMemcpyAsync(code, code_host, n * 16, cudaMemcpyHostToDevice, s));
+    int st = h2d(code, code_host, n * 16, s);
+    if (st != ML_OK) { pfree(code, s); return st; }
     return fri_init_owned(out, code, n, true, t, s);
 }
 static int check_gen_pows(const ml_fri* f, const uint8_t* gen_pows, size_t gen_pows_len) {
     if (!gen_pows) return ML_OK;
     if (gen_pows_len != ((size_t)1 << f->log_n0)) { set_error("gen_pows.len() must equal the domain size"); return ML_ERR_SIZE; }
+    // The kernels read their own root tables (powers of pow_2_generator(log2 domain)), not this array, so a caller-supplied table is
+    // only accepted if it IS that table.  Checked at [0], [1], [2], [len/2], [len-1] and 16 spread positions (host scalar pow): a table
+    // of the right length that disagrees anywhere else would be a table the reference's own callers never build (they all pass
+    // pow_2_generator_powers, src/fri/mod.rs:352, multilinear_pcs.rs:98); the restriction is stated in the header.
     hfe w;
     hfe_pow2_generator((uint64_t)f->log_n0, &w);
-    if (gen_pows_len > 1 && hfe_load(gen_pows + 16) != w) { set_error("gen_pows[1] is not pow_2_generator(log2 domain)"); return ML_ERR_GENERATOR; }
+    size_t probe[21] = {0, 1, 2, gen_pows_len / 2, gen_pows_len - 1};
+    for (int i = 0; i < 16; i++) probe[5 + i] = (size_t)(((unsigned __int128)gen_pows_len * (2 * i + 1)) / 33) ^ (size_t)(i * 2654435761u % 97);
+    for (size_t idx : probe) {
+        if (idx >= gen_pows_len) continue;
+        if (hfe_load(gen_pows + 16 * idx) != hfe_pow(w, (hfe)idx)) {
+            set_error("gen_pows[%zu] is not pow_2_generator(%d)^%zu: only the domain's own power table is supported", idx, f->log_n0, idx);
+            return ML_ERR_GENERATOR;
+        }
+    }
     return ML_OK;
 }
 int ml_fri_fold_step(ml_fri* f, const uint8_t* gen_pows, size_t gen_pows_len, size_t k, const uint8_t r[16], ml_transcript* t) {

@@ -7,8 +7,8 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "multilinear_b200.h")).read()
+def declared_symbols(header="multilinear_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(ml_[a-z0-9_]+)\s*\(", text)))
 
@@ -27,6 +27,20 @@ def test_library_exports_every_declared_symbol(ml):
     assert len(names) > 90
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
+
+
+def test_instrumentation_is_outside_the_product_header(ml):
+    """profiling / microbenchmark entry points are declared in multilinear_b200_instr.h only; the microbenchmark kernels are
+    not linked into the product library"""
+    import multilinear_b200
+    product = set(declared_symbols())
+    instr = set(declared_symbols("multilinear_b200_instr.h"))
+    assert instr and not (product & instr)
+    assert not [n for n in product if "profile" in n or "microbench" in n or "trace" in n]
+    lib = ctypes.CDLL(multilinear_b200.lib_path())
+    assert not hasattr(lib, "ml_microbench")
+    ilib = ctypes.CDLL(os.path.join(os.path.dirname(multilinear_b200.lib_path()), "libmlb_instr.so"))
+    assert all(hasattr(lib, n) or hasattr(ilib, n) for n in instr)
 
 
 def test_no_torch_types_in_signatures():
