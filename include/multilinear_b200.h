@@ -32,6 +32,7 @@ extern "C" {
 
 #define ML_LOG_BLOWUP 1    /* src/fri/mod.rs:16 */
 #define ML_NUM_QUERIES 128 /* src/fri/mod.rs:17 */
+#define ML_MAX_PEERS 16   /* ranks of a sharded prover */
 
 enum {
     ML_OK = 0,
@@ -42,7 +43,8 @@ enum {
     ML_ERR_GENERATOR = 5,    /* `gen` is not a primitive n-th root of unity (the DIT network assumes it) */
     ML_ERR_CUDA = 6,         /* CUDA runtime error / no device / extension not built for this GPU */
     ML_ERR_ALLOC = 7,
-    ML_ERR_ARG = 8
+    ML_ERR_ARG = 8,
+    ML_ERR_PEER = 9          /* sharded prover: a peer rank's memory cannot be mapped, or a peer did not arrive in time */
 };
 /* verifier results (FriProofError, src/fri/mod.rs:251-258) */
 enum {
@@ -269,7 +271,37 @@ int ml_wsumcheck_fold(ml_wsumcheck *w, const uint8_t r[16]);                    
 int ml_wsumcheck_compute_polynomials(ml_wsumcheck *w, size_t composition_degree, ml_transcript *t, const uint8_t sum[16],
                                      uint8_t *coeffs_out, uint8_t *randoms_out);                     /* :147-202 */
 
-/* ---- batched commit, sharded (BASELINE config 5): one rank's share of `Merkle::batch_commit`
+/* ---- BatchedPCSProof::prove sharded over the GPUs of one box (BASELINE config 5; batched_pcs.rs:130-180) ----
+ * G ranks (a power of two <= ML_MAX_PEERS), one GPU each.  Rank g encodes the polynomials j with j mod G == g, then owns leaf rows
+ * [g*n/G, (g+1)*n/G) of the batched tree: their hashing, fingerprints, first fold and openings.  All exchange is kernels storing
+ * into the owner's peer-visible arena over NVLink followed by device-side flags — no NCCL, no host barrier (csrc/shard.cu).
+ * A handle hosts the ranks of ONE process:
+ *   - all G ranks (n_local == world): a single-process caller such as the Rust crate; ready after ml_shard_create.  Devices may
+ *     repeat (virtual ranks on one GPU, used by the tests);
+ *   - one rank (n_local == 1): one process per GPU.  Every process exports its record (ml_shard_export), the caller all-gathers the
+ *     records with whatever transport it has (72 bytes per rank) and hands all of them to ml_shard_connect.
+ * The proof is byte-identical to ml_batched_pcs_prove's.  Calls on one handle are sequential; in the multi-process mode every
+ * rank must make the same calls in the same order (a rank that does not arrive makes the others fail with ML_ERR_PEER after
+ * MLB_SHARD_TIMEOUT_S seconds, default 20). */
+typedef struct ml_shard ml_shard;
+int ml_shard_create(int world, int n_local, const int *local_ranks, const int *local_devices, size_t n_polys, size_t n_vars, ml_shard **out);
+void ml_shard_free(ml_shard *sh);      /* multi-process: all ranks must have returned from their last call (caller's barrier) */
+size_t ml_shard_record_bytes(void);    /* 72 */
+int ml_shard_num_local(const ml_shard *sh);
+int ml_shard_export(ml_shard *sh, uint8_t *records_out /* num_local * 72 */);
+int ml_shard_connect(ml_shard *sh, const uint8_t *records, size_t n_records /* world */);
+void *ml_shard_stream(const ml_shard *sh, int local_index);   /* the local rank's main stream (for CUDA-event timing) */
+size_t ml_shard_arena_bytes(const ml_shard *sh);
+/* local_evals_dev: for every local rank in handle order, its n_polys/world polynomials (device pointers, n = 2^n_vars elements
+ * each) in increasing global index (rank, rank + world, ...); they must be complete before the call (no stream ordering). */
+int ml_shard_batch_commit_dev(ml_shard *sh, const void *const *local_evals_dev, uint8_t root_out[32]); /* Merkle::batch_commit root of the encoded batch */
+int ml_shard_batched_pcs_prove_dev(ml_shard *sh, const uint8_t *inputs, size_t n_vars, const uint8_t *outputs, size_t n_polys,
+                                   const void *const *local_evals_dev, ml_transcript *t, ml_bpcs_proof **out /* NULL unless rank 0 is local */);
+/* host pointers, evals[j] for all n_polys polynomials; needs a handle that hosts every rank — the drop-in for batched_pcs.rs:130 */
+int ml_shard_batched_pcs_prove(ml_shard *sh, const uint8_t *inputs, size_t n_vars, const uint8_t *outputs, size_t n_polys,
+                               const uint8_t *const *evals, ml_transcript *t, ml_bpcs_proof **out);
+
+/* ---- batched commit building blocks (round-1 API, kept): one rank's share of `Merkle::batch_commit`
  * (merkle_tree/mod.rs:110-131) over leaf range [leaf_begin, leaf_begin+leaf_count) of all codes.
  * codes_dev[j] points at code j's rows for this range laid out as pairs: leaf_count x 32 bytes.
  * Writes the subtree root of the range (leaf_count a power of two); ranks then all-gather the roots
@@ -286,7 +318,6 @@ int ml_batched_leaf_subtree_root_dev(const void *const *pairs_dev, size_t n_code
  * through NVLink peer mappings (no send buffer, no collective).  peer_bases[g] is rank g's receive buffer
  * ([global polynomial][row][32 B], rows = n_code/2/n_ranks) as mapped into this process (own buffer for g == rank);
  * max_ctas bounds the grid so the store pass shares the GPU with the next polynomial's NTT (0 = default). */
-#define ML_MAX_PEERS 16
 int ml_pack_pairs_peer_dev(const void *code_dev, size_t n_code, size_t n_ranks, size_t global_poly, void *const *peer_bases, unsigned max_ctas, void *stream);
 /* peer-visible device buffers (CUDA IPC): owner allocates + publishes the 64-byte handle; peers map / unmap it */
 int ml_ipc_alloc(size_t bytes, void **dev_out, uint8_t handle_out[64]);

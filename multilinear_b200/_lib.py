@@ -13,7 +13,7 @@ _LIB = None
 
 ML_OK = 0
 ERR_NAMES = {1: "ML_ERR_NOT_POW2", 2: "ML_ERR_SIZE", 3: "ML_ERR_OUT_OF_RANGE", 4: "ML_ERR_NOT_RS_CODE", 5: "ML_ERR_GENERATOR",
-             6: "ML_ERR_CUDA", 7: "ML_ERR_ALLOC", 8: "ML_ERR_ARG"}
+             6: "ML_ERR_CUDA", 7: "ML_ERR_ALLOC", 8: "ML_ERR_ARG", 9: "ML_ERR_PEER"}
 
 
 class MlError(RuntimeError):
@@ -38,10 +38,10 @@ _EXC = {1: NotPowerOfTwo, 2: SizeMismatch, 4: NotRsCode}
 
 _SIZE_T_FUNCS = ["ml_merkle_num_layers", "ml_merkle_layer_len", "ml_fri_num_trees", "ml_fri_proof_num_commitments",
                  "ml_fri_proof_serialized_len", "ml_sumcheck_height", "ml_wsumcheck_height", "ml_wsumcheck_width", "ml_pcs_proof_num_rounds", "ml_bfri_proof_num_commitments",
-                 "ml_bfri_proof_serialized_len", "ml_bpcs_proof_num_rounds"]
-_PTR_FUNCS = ["ml_pcs_proof_fri", "ml_bpcs_proof_fri"]
+                 "ml_bfri_proof_serialized_len", "ml_bpcs_proof_num_rounds", "ml_shard_record_bytes", "ml_shard_arena_bytes"]
+_PTR_FUNCS = ["ml_pcs_proof_fri", "ml_bpcs_proof_fri", "ml_shard_stream"]
 _VOID_FUNCS = ["ml_transcript_free", "ml_merkle_free", "ml_fri_free", "ml_fri_proof_free", "ml_sumcheck_free", "ml_wsumcheck_free", "ml_pcs_proof_free",
-               "ml_bfri_proof_free", "ml_bpcs_proof_free"]
+               "ml_bfri_proof_free", "ml_bpcs_proof_free", "ml_shard_free"]
 
 
 def lib_path():

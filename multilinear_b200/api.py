@@ -694,6 +694,87 @@ class BatchedPCSProof:
         return PCSProof(h, batched=True)
 
 
+class ShardedBatchedProver:
+    """BatchedPCSProof::prove sharded over the GPUs of one box (ml_shard_*, csrc/shard.cu).  A handle hosts the ranks of one
+    process: all of them (single_process; devices may repeat = virtual ranks on one GPU) or one (one_rank; the records of all
+    processes are all-gathered by the caller's transport and passed to connect)."""
+
+    def __init__(self, h, world, local_ranks, n_polys, n_vars):
+        self.h, self.world, self.local_ranks, self.n_polys, self.n_vars = h, world, list(local_ranks), n_polys, n_vars
+
+    @staticmethod
+    def _create(world, ranks, devices, n_polys, n_vars):
+        h = C.c_void_p()
+        ra, da = (C.c_int * len(ranks))(*ranks), (C.c_int * len(devices))(*devices)
+        check(load().ml_shard_create(C.c_int(world), C.c_int(len(ranks)), ra, da, _sz(n_polys), _sz(n_vars), C.byref(h)))
+        return ShardedBatchedProver(h, world, ranks, n_polys, n_vars)
+
+    @staticmethod
+    def single_process(devices, n_polys, n_vars):
+        return ShardedBatchedProver._create(len(devices), list(range(len(devices))), list(devices), n_polys, n_vars)
+
+    @staticmethod
+    def one_rank(rank, world, device, n_polys, n_vars):
+        return ShardedBatchedProver._create(world, [rank], [device], n_polys, n_vars)
+
+    def export(self):
+        out = np.empty(72 * len(self.local_ranks), dtype=np.uint8)
+        check(load().ml_shard_export(self.h, _p(out)))
+        return out.tobytes()
+
+    def connect(self, records):
+        buf = np.frombuffer(bytes(records), dtype=np.uint8).copy()
+        check(load().ml_shard_connect(self.h, _p(buf), _sz(len(buf) // 72)))
+
+    def connect_over(self, dist, device):
+        """all-gather the IPC records over a torch.distributed process group (the only use of the collective library)"""
+        import torch
+        mine = torch.tensor(list(self.export()), dtype=torch.uint8, device=device)
+        allr = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+        dist.all_gather(allr, mine)
+        self.connect(b"".join(bytes(r.cpu().numpy().tobytes()) for r in allr))
+
+    def stream(self, local_index=0):
+        return load().ml_shard_stream(self.h, C.c_int(local_index))
+
+    def local_polys(self):
+        """global polynomial indices in the order local_evals must be given: for each local rank, rank, rank + world, ..."""
+        return [r + l * self.world for r in self.local_ranks for l in range(self.n_polys // self.world)]
+
+    def batch_commit_dev(self, local_evals_ptrs):
+        ptrs = (C.c_void_p * len(local_evals_ptrs))(*local_evals_ptrs)
+        root = np.empty(32, dtype=np.uint8)
+        check(load().ml_shard_batch_commit_dev(self.h, ptrs, _p(root)))
+        return root.tobytes()
+
+    def prove_dev(self, claim_inputs, claim_outputs, local_evals_ptrs, transcript):
+        i, o = as_elems(claim_inputs), as_elems(claim_outputs)
+        ptrs = (C.c_void_p * len(local_evals_ptrs))(*local_evals_ptrs)
+        h = C.c_void_p()
+        check(load().ml_shard_batched_pcs_prove_dev(self.h, _p(i), _sz(i.shape[0]), _p(o), _sz(o.shape[0]), ptrs, transcript.h, C.byref(h)))
+        return PCSProof(h, batched=True) if h.value else None
+
+    def prove(self, claim_inputs, claim_outputs, polys, transcript):
+        """host arrays for all polynomials (needs a single-process handle) — the drop-in for batched_pcs.rs:130"""
+        i, o = as_elems(claim_inputs), as_elems(claim_outputs)
+        ps = [p.evals if isinstance(p, MultilinearPolynomialEvals) else as_elems(p) for p in polys]
+        ptrs = (C.c_void_p * len(ps))(*[p.ctypes.data for p in ps])
+        h = C.c_void_p()
+        check(load().ml_shard_batched_pcs_prove(self.h, _p(i), _sz(i.shape[0]), _p(o), _sz(len(ps)), ptrs, transcript.h, C.byref(h)))
+        return PCSProof(h, batched=True)
+
+    def free(self):
+        if self.h is not None and self.h.value:
+            load().ml_shard_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 _INSTR = None
 
 

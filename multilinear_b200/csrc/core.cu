@@ -215,11 +215,8 @@ int ml_profile_get_max(int id, double* mean_ms, uint64_t* launches, double* alg_
     return ML_OK;
 }
 int ml_stream_create(void** out) {
-    Ctx* ctx;
-    MLB_TRY(get_ctx(&ctx));  // sets the default pool's attributes before the first allocation on this device
     cudaStream_t s;
-    MLB_CUDA(cudaStreamCreate(&s));  // blocking stream: ordered against the legacy default stream (event timing in bench.py)
-    register_stream_pool(ctx->device, s);
+    MLB_TRY(lib_stream_create(&s, false));  // blocking stream: ordered against the legacy default stream (event timing in bench.py)
     *out = (void*)s;
     return ML_OK;
 }
@@ -272,8 +269,20 @@ int ml_pool_stats(uint64_t* reserved_bytes, uint64_t* used_bytes) {
     *reserved_bytes = res; *used_bytes = used;
     return ML_OK;
 }
-int ml_stream_destroy(void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
+int ml_stream_destroy(void* stream) { return lib_stream_destroy((cudaStream_t)stream); }
+}  // extern "C"
+namespace mlb {
+int lib_stream_create(cudaStream_t* out, bool non_blocking) {
+    Ctx* ctx;
+    MLB_TRY(get_ctx(&ctx));  // sets the default pool's attributes before the first allocation on this device
+    cudaStream_t s;
+    if (non_blocking) MLB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    else MLB_CUDA(cudaStreamCreate(&s));
+    register_stream_pool(ctx->device, s);
+    *out = s;
+    return ML_OK;
+}
+int lib_stream_destroy(cudaStream_t s) {
     MLB_CUDA(cudaStreamSynchronize(s));
     {   // drop the stream's private pool (the driver defers the release until its last allocation is freed)
         int dev = 0;
@@ -288,6 +297,8 @@ int ml_stream_destroy(void* stream) {
     MLB_CUDA(cudaStreamDestroy(s));
     return ML_OK;
 }
+}  // namespace mlb
+extern "C" {
 int ml_stream_synchronize(void* stream) { MLB_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return ML_OK; }
 int ml_set_thread_stream(void* stream, int enable) {
     tl_stream = (cudaStream_t)stream;

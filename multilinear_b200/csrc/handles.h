@@ -57,6 +57,7 @@ struct ml_fri_proof {
 struct ml_sumcheck {
     mlb::fe* matrix = nullptr;
     mlb::fe* delta = nullptr;
+    bool owns_matrix = true;  // false: the matrix lives in a sharded prover's peer-visible arena
     size_t height = 0;
     cudaStream_t stream = nullptr;
 };

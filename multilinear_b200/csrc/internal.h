@@ -134,6 +134,10 @@ struct Ctx {
 int get_ctx(Ctx** out);  // context of the current device (lazily created)
 // stream used by host-pointer entry points: the calling thread's override (ml_set_thread_stream) or the context stream
 cudaStream_t lib_stream(Ctx* ctx);
+// a stream owned by the library with its private allocation pool (what ml_stream_create hands out); non_blocking: not ordered
+// against the legacy default stream
+int lib_stream_create(cudaStream_t* out, bool non_blocking);
+int lib_stream_destroy(cudaStream_t s);
 int get_root_tables(Ctx* ctx, int log_n, cudaStream_t s, const RootTables** out);
 
 // stream-ordered scratch allocation
@@ -165,6 +169,7 @@ int merkle_rs_launch(const fe* code, size_t n_code, uint8_t* digests, cudaStream
 int merkle_bytes_launch(const uint8_t* const* data_dev_ptrs, size_t n_batches, size_t item_bytes, size_t n_items, uint8_t* digests, cudaStream_t s);
 int merkle_batched_rs_launch(const fe* const* codes_dev_ptrs, size_t n_codes, size_t n_code, uint8_t* digests, cudaStream_t s);
 int merkle_batched_pairs_launch(const uint8_t* const* pairs_dev_ptrs, size_t n_codes, size_t n_leaves, uint8_t* digests, cudaStream_t s);
+int merkle_batched_pairs_strided_launch(const uint8_t* pairs_base, size_t n_codes, size_t n_leaves, uint8_t* digests, cudaStream_t s);
 int merkle_upper_launch(uint8_t* digests, size_t n_leaves, cudaStream_t s);  // layers 1.. from layer 0
 // fri.cu — r_dev (optional): device pointer to {r, r/2} written by a transcript kernel; overrides the host value r
 int fri_fold_launch(Ctx* ctx, const fe* cur, size_t n_cur, fe* next, hfe r, const fe* r_dev, size_t k, int log_n0, cudaStream_t s);

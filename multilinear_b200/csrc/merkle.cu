@@ -183,9 +183,12 @@ static int merkle_top_launch(uint8_t* digests, size_t n_leaves, int layer, cudaS
 // Two 32-byte pairs fill one block, so B pairs take ceil((B+1)/2) compressions (33 for B = 64).
 // PAIRS = false: src[j] is code j (n_code elements), pair = (code[i], code[i + n_leaves]);
 // PAIRS = true : src[j] is an array of n_leaves ReedSolomonPairs (32 bytes each).
-template <bool PAIRS>
+// STRIDED (with PAIRS): the pair arrays are equally spaced, src[j] = (const fe*)strided_base + j * stride_elems — the layout of a
+// sharded prover's receive buffer ([polynomial][row][32 B]), which needs no pointer table.
+template <bool PAIRS, bool STRIDED = false>
 __global__ void __launch_bounds__(128) merkle_batched_kernel(const fe* const* __restrict__ src, int n_codes, size_t n_leaves,
-                                                             uint8_t* __restrict__ digests) {
+                                                             uint8_t* __restrict__ digests, const fe* __restrict__ strided_base = nullptr,
+                                                             size_t stride_elems = 0) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_leaves) return;
     uint32_t st[8];
@@ -193,13 +196,13 @@ __global__ void __launch_bounds__(128) merkle_batched_kernel(const fe* const* __
     uint32_t w[16];
     const unsigned long long bits = (unsigned long long)n_codes * 256ull;
     for (int j = 0; j < n_codes; j += 2) {
-        const fe* c0 = src[j];
+        const fe* c0 = STRIDED ? strided_base + (size_t)j * stride_elems : src[j];
         uint4 x0 = PAIRS ? __ldg(reinterpret_cast<const uint4*>(c0 + 2 * i)) : __ldg(reinterpret_cast<const uint4*>(c0 + i));
         uint4 y0 = PAIRS ? __ldg(reinterpret_cast<const uint4*>(c0 + 2 * i + 1)) : __ldg(reinterpret_cast<const uint4*>(c0 + i + n_leaves));
         sha_words_from_le(x0, w);
         sha_words_from_le(y0, w + 4);
         if (j + 1 < n_codes) {
-            const fe* c1 = src[j + 1];
+            const fe* c1 = STRIDED ? strided_base + (size_t)(j + 1) * stride_elems : src[j + 1];
             uint4 x1 = PAIRS ? __ldg(reinterpret_cast<const uint4*>(c1 + 2 * i)) : __ldg(reinterpret_cast<const uint4*>(c1 + i));
             uint4 y1 = PAIRS ? __ldg(reinterpret_cast<const uint4*>(c1 + 2 * i + 1)) : __ldg(reinterpret_cast<const uint4*>(c1 + i + n_leaves));
             sha_words_from_le(x1, w + 8);
@@ -286,6 +289,18 @@ int merkle_batched_pairs_launch(const uint8_t* const* pairs, size_t n_codes, siz
     {
         ProfScope prof(PROF_MERKLE_LEAF, (32.0 * (double)n_codes + 32.0) * (double)n_leaves, s);
         merkle_batched_kernel<true><<<(unsigned)((n_leaves + 127) / 128), 128, 0, s>>>((const fe* const*)pairs, (int)n_codes, n_leaves, digests);
+        MLB_KERNEL_CHECK();
+    }
+    return upper_from(digests, n_leaves, 0, s);
+}
+// pair arrays at pairs_base + j * n_leaves * 32 bytes (one per code); layers above the leaves optional (a caller that shares the
+// stream with other work may want the leaf pass alone)
+int merkle_batched_pairs_strided_launch(const uint8_t* pairs_base, size_t n_codes, size_t n_leaves, uint8_t* digests, cudaStream_t s) {
+    if (n_leaves == 0 || n_codes == 0) return ML_ERR_NOT_POW2;
+    {
+        ProfScope prof(PROF_MERKLE_LEAF, (32.0 * (double)n_codes + 32.0) * (double)n_leaves, s);
+        merkle_batched_kernel<true, true><<<(unsigned)((n_leaves + 127) / 128), 128, 0, s>>>(nullptr, (int)n_codes, n_leaves, digests,
+                                                                                              (const fe*)pairs_base, 2 * n_leaves);
         MLB_KERNEL_CHECK();
     }
     return upper_from(digests, n_leaves, 0, s);

@@ -6,10 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
-#include "field.cuh"
-#include "handles.h"
-#include "internal.h"
-#include "transcript.cuh"
+#include "prover_internal.h"
 
 using namespace mlb;
 
@@ -18,17 +15,7 @@ using namespace mlb;
     MLB_TRY(get_ctx(&ctx));
 #define ST(stream_arg) ((cudaStream_t)(stream_arg))
 
-namespace {
-
-struct Scratch {
-    void* p = nullptr;
-    cudaStream_t s;
-    explicit Scratch(cudaStream_t st) : s(st) {}
-    int alloc(size_t bytes) { return dev_alloc_async(&p, bytes, s); }
-    void* release() { void* r = p; p = nullptr; return r; }
-    ~Scratch() { if (p) cudaFreeAsync(p, s); }
-    template <class T> T* as() { return (T*)p; }
-};
+namespace mlbp {
 
 // handle-owned buffers come from the stream-ordered pool (cudaMalloc/cudaFree would serialise the device per layer)
 int pmalloc(void** p, size_t bytes, cudaStream_t s) { return dev_alloc_async(p, bytes, s); }
@@ -38,7 +25,7 @@ void pfree(void* p, cudaStream_t s) { if (p) cudaFreeAsync(p, s); }
 struct TraceRec { size_t tid; const char* tag; double t; };
 static std::mutex g_trace_mu;
 static std::vector<TraceRec> g_trace;
-static inline void trace(const char* tag) {
+void trace(const char* tag) {
     static const bool on = getenv("MLB_TRACE") != nullptr;
     if (!on) return;
     const double t = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -54,7 +41,6 @@ static void trace_dump_impl() {
     for (const TraceRec& r : g_trace) fprintf(stderr, "TRACE %03zu %-14s %9.3f ms\n", r.tid, r.tag, (r.t - t0) * 1e3);
     g_trace.clear();
 }
-static int stream_wait_blocking(cudaStream_t s);
 // Host -> device upload.  Large uploads from concurrent callers to ONE device are serialised (one at a time, each waited for
 // under that device's lock): a copy engine shared by n uploads finishes all of them late, so n commits submitted together would all
 // start their NTT after the LAST byte of the LAST input arrived and then run in lock-step — copy phase with idle SMs, compute phase
@@ -86,7 +72,7 @@ int h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
 // and one process per GPU the default spin-wait of cudaStreamSynchronize keeps (streams x GPUs) host cores busy — more than an
 // 8-GPU box has, which starved the threads still enqueueing kernels (8 GPUs: 68.6 ms per step instead of 53.8).
 // A blocking-sync event lets the thread sleep until the GPU signals.
-static int stream_wait_blocking(cudaStream_t s) {
+int stream_wait_blocking(cudaStream_t s) {
     static const bool spin = getenv("MLB_SPIN_SYNC") != nullptr;
     if (spin) { MLB_CUDA(cudaStreamSynchronize(s)); return ML_OK; }
     thread_local cudaEvent_t ev = nullptr;
@@ -107,8 +93,6 @@ int d2h_sync(void* dst, const void* src, size_t bytes, cudaStream_t s) {
     return stream_wait_blocking(s);
 }
 int fri_push_layer(ml_fri* f, fe* code, size_t n, bool owns_code, cudaStream_t s, bool build_tree);
-int fold_chain_dev(Ctx* ctx, ml_fri* f, struct BatchedFri* b, ml_sumcheck* sc, hfe prev, hfe* sc_out, size_t k_start, bool pending,
-                   ml_transcript* t, cudaStream_t s);
 void absorb_fe(ml_transcript* t, hfe x) {
     uint8_t b[16];
     hfe_store(b, x);
@@ -405,7 +389,7 @@ int sumcheck_round(Ctx* ctx, ml_sumcheck* sc, size_t total_degree, hfe* previous
 }
 void free_sumcheck(ml_sumcheck* s) {
     if (!s) return;
-    pfree(s->matrix, s->stream);
+    if (s->owns_matrix) pfree(s->matrix, s->stream);
     pfree(s->delta, s->stream);
     delete s;
 }
@@ -454,8 +438,6 @@ int encode_poly(Ctx* ctx, const fe* evals_dev, size_t n, fe** code_out, cudaStre
 }
 
 // ------------------------------------------------------------------ sync-free fold chain (device transcript)
-struct BatchedFri;
-int bfri_first_fold_dev(Ctx* ctx, BatchedFri* b, const fe* r_dev, fe** next_out, size_t* half_n_out, cudaStream_t s);
 
 // build the tree of a layer without reading the root back (the chain absorbs it on the device)
 int fri_push_layer(ml_fri* f, fe* code, size_t n, bool owns_code, cudaStream_t s, bool build_tree) {
@@ -485,7 +467,7 @@ uint8_t* layer_root_ptr(const ml_fri::Layer& L) {
 //   sc/prev : sumcheck tables + running claim for the PCS interleave (nullptr/unused for plain FRI)
 //   sc_out  : host array receiving (c1, c2) per round from k_start on
 // On return every layer root, last_element and the host transcript are up to date.
-int fold_chain_dev(Ctx* ctx, ml_fri* f, BatchedFri* b, ml_sumcheck* sc, hfe prev, hfe* sc_out, size_t k_start, bool pending,
+int fold_chain_dev(Ctx* ctx, ml_fri* f, const ChainHooks* hooks, ml_sumcheck* sc, hfe prev, hfe* sc_out, size_t k_start, bool pending,
                    ml_transcript* t, cudaStream_t s) {
     const size_t total_steps = (size_t)f->log_n0 - ML_LOG_BLOWUP;
     if (k_start >= total_steps) {
@@ -509,11 +491,16 @@ int fold_chain_dev(Ctx* ctx, ml_fri* f, BatchedFri* b, ml_sumcheck* sc, hfe prev
     fe* sc_dev = (fe*)(base + off_sc);
     fe* partials = (fe*)(base + off_part);
     MLB_CUDA(cudaMemsetAsync(base, 0, off_part, s));
-    MLB_TRY(h2d(tr_dev, &t->sha, sizeof(DevTranscript), s));
+    if (hooks && hooks->tr_dev) MLB_CUDA(cudaMemcpyAsync(tr_dev, hooks->tr_dev, sizeof(DevTranscript), cudaMemcpyDeviceToDevice, s));
+    else MLB_TRY(h2d(tr_dev, &t->sha, sizeof(DevTranscript), s));
     if (sc) {
-        uint8_t pb[16];
-        hfe_store(pb, prev);
-        MLB_TRY(h2d(prev_dev, pb, 16, s));
+        if (hooks && hooks->prev_dev) {
+            MLB_CUDA(cudaMemcpyAsync(prev_dev, hooks->prev_dev, 16, cudaMemcpyDeviceToDevice, s));
+        } else {
+            uint8_t pb[16];
+            hfe_store(pb, prev);
+            MLB_TRY(h2d(prev_dev, pb, 16, s));
+        }
     }
     const RootTables* rt;
     MLB_TRY(get_root_tables(ctx, f->log_n0, s, &rt));
@@ -577,9 +564,10 @@ int fold_chain_dev(Ctx* ctx, ml_fri* f, BatchedFri* b, ml_sumcheck* sc, hfe prev
         pending = false;
         // ---- fold
         fe* next = nullptr;
+        bool owns_next = true;
         if (batched_round) {
-            size_t hn = 0;
-            MLB_TRY(bfri_first_fold_dev(ctx, b, r_dev, &next, &hn, s));
+            if (!hooks || !hooks->first_fold) { set_error("fold chain: empty FriProverData without a first-fold hook"); return ML_ERR_ARG; }
+            MLB_TRY(hooks->first_fold(r_dev, &next, &owns_next));
         } else {
             MLB_TRY(pmalloc((void**)&next, half_n * 16, s));
             int st = fri_fold_launch(ctx, f->layers.back().code, n, next, 0, r_dev, k, f->log_n0, s);
@@ -587,14 +575,14 @@ int fold_chain_dev(Ctx* ctx, ml_fri* f, BatchedFri* b, ml_sumcheck* sc, hfe prev
         }
         if (half_n == ((size_t)1 << ML_LOG_BLOWUP)) {  // only reachable from a batched first fold of a 4-element domain
             int st = chain_last_launch(next, tr_dev, last_dev, status_dev, s);
-            pfree(next, s);
+            if (owns_next) pfree(next, s);
             MLB_TRY(st);
             used_tail = true;
             k = total_steps;
             break;
         }
-        int st = fri_push_layer(f, next, half_n, true, s, true);
-        if (st != ML_OK) { pfree(next, s); return st; }
+        int st = fri_push_layer(f, next, half_n, owns_next, s, true);
+        if (st != ML_OK) { if (owns_next) pfree(next, s); return st; }
         pending = true;
     }
     if (pending) {  // chain ended on a committed layer (cannot happen for well-formed sizes, kept for safety)
@@ -906,7 +894,8 @@ int bfri_verify_queries(const ml_bfri_proof* p, ml_transcript* t, const hfe* rs,
     return memcmp(lr, p->last_random, 32) == 0 ? ML_V_OK : ML_V_LAST_RANDOM;
 }
 
-}  // namespace
+}  // namespace mlbp
+using namespace mlbp;
 
 extern "C" {
 void ml_trace_dump(void) { trace_dump_impl(); }
@@ -1553,7 +1542,9 @@ int ml_batched_fri_prove(const uint8_t* const* codes, size_t n_codes, size_t n, 
     }
     MLB_TRY(bfri_init(&b, t, s));
     // batched first fold (:193-195) + the remaining fold steps (:198-201), transcript advanced on the device
-    MLB_TRY(fold_chain_dev(ctx, b.fri, &b, nullptr, 0, nullptr, 0, false, t, s));
+    ChainHooks hooks;
+    hooks.first_fold = [&](const fe* r_dev, fe** next, bool* owns) { *owns = true; size_t hn = 0; return bfri_first_fold_dev(ctx, &b, r_dev, next, &hn, s); };
+    MLB_TRY(fold_chain_dev(ctx, b.fri, &hooks, nullptr, 0, nullptr, 0, false, t, s));
     ml_bfri_proof* p = new ml_bfri_proof();
     int st = bfri_assemble(&b, t, p, s);
     if (st != ML_OK) { delete p; return st; }
@@ -1625,7 +1616,9 @@ int ml_batched_pcs_prove_dev(const uint8_t* inputs, size_t n_vars, const uint8_t
     const size_t num_steps = ilog2(domain) - ML_LOG_BLOWUP;  // :90
     p->sumcheck.resize(2 * num_steps);
     hfe prev = fingerprint_host(fr, outs.data(), n_polys);   // :92-94
-    if (st == ML_OK) st = fold_chain_dev(ctx, b.fri, &b, sc, prev, p->sumcheck.data(), 0, false, t, s);  // :100-123
+    ChainHooks hooks;
+    hooks.first_fold = [&](const fe* r_dev, fe** next, bool* owns) { *owns = true; size_t hn = 0; return bfri_first_fold_dev(ctx, &b, r_dev, next, &hn, s); };
+    if (st == ML_OK) st = fold_chain_dev(ctx, b.fri, &hooks, sc, prev, p->sumcheck.data(), 0, false, t, s);  // :100-123
     if (st == ML_OK) st = bfri_assemble(&b, t, &p->fri, s);  // :155-173
     free_sumcheck(sc);
     if (st != ML_OK) { delete p; return st; }

@@ -496,6 +496,55 @@ def test_sharded_batch_commit_single_gpu(ml, oracle, mode):
     assert root == oracle.merkle_batch_commit(datas).root()
 
 
+# ------------------------------------------------------------------ sharded BatchedPCSProof::prove (ml_shard_*, config 5)
+@pytest.mark.parametrize("world,nv,B", [(1, 6, 3), (2, 6, 4), (2, 10, 6), (4, 12, 8), (8, 13, 16), (8, 16, 8)])
+def test_sharded_batched_pcs_prove_virtual_ranks_vs_oracle(ml, oracle, world, nv, B):
+    """G ranks hosted by one process on ONE GPU (virtual ranks, phases enqueued in lock step): the proof bytes, the sumcheck
+    polynomials and the transcript equal the oracle's BatchedPCSProof::prove; so does the unsharded CUDA prover's proof"""
+    rng = random.Random(world * 1000 + nv * 10 + B)
+    polys = [oracle.synthetic(3000 * B + j, 1 << nv) for j in range(B)]
+    inp = fe_arr([rng.randrange(M) for _ in range(nv)])
+    outs = fe_arr([oracle.mle_evals_evaluate(p, inp) for p in polys])
+    sh = ml.ShardedBatchedProver.single_process([0] * world, B, nv)
+    t, ot = ml.Transcript(), oracle.transcript()
+    proof = sh.prove(inp, outs, polys, t)
+    oproof, st = oracle.batched_pcs_prove(inp, outs, polys, ot)
+    assert st == 0 and proof.fri_proof.serialize() == oproof.fri.blob
+    assert [c for nz in proof.sumcheck_polynomials for c in nz] == oproof.sumcheck
+    assert t.random() == ot.random() and proof.verify(ml.Transcript()) == 0
+    # a second call on the same handle (epoch 2) gives the same bytes
+    t2 = ml.Transcript()
+    assert sh.prove(inp, outs, polys, t2).fri_proof.serialize() == oproof.fri.blob and t2.random() == ot.random()
+    sh.free()
+
+
+def test_sharded_batch_commit_root_and_errors(ml, oracle):
+    import ctypes as C
+    from multilinear_b200._lib import MlError
+    nv, B, world = 11, 8, 4
+    n = 1 << nv
+    polys = [oracle.synthetic(7000 + j, n) for j in range(B)]
+    g = oracle.pow2_generator(nv + 1)
+    datas = []
+    for p in polys:
+        code = oracle.reed_solomon(oracle.bit_reverse(oracle.to_coefficient(p)), g)
+        datas.append(np.concatenate([code[:n], code[n:]], axis=1))
+    want = oracle.merkle_batch_commit(datas).root()
+    sh = ml.ShardedBatchedProver.single_process([0] * world, B, nv)
+    bufs = [ml.DeviceBuffer.from_host(polys[j]) for j in sh.local_polys()]
+    assert sh.batch_commit_dev([b.ptr.value for b in bufs]) == want
+    assert sh.batch_commit_dev([b.ptr.value for b in bufs]) == want
+    sh.free()
+    with pytest.raises(MlError):
+        ml.ShardedBatchedProver.single_process([0] * 3, B, nv)      # world must be a power of two
+    with pytest.raises(MlError):
+        ml.ShardedBatchedProver.single_process([0] * 4, 6, nv)      # polynomials must split evenly
+    one = ml.ShardedBatchedProver.one_rank(1, 2, 0, 4, 6)           # a rank whose peers were never connected refuses to run
+    with pytest.raises(MlError):
+        one.batch_commit_dev([0, 0])
+    one.free()
+
+
 # ------------------------------------------------------------------ oracle parity AT the BASELINE sizes (configs 2-5)
 # The oracle needs seconds per case on the box's host cores (all threads); every comparison is bit-exact.
 @pytest.fixture(scope="module")
@@ -609,6 +658,10 @@ def test_atsize_config5_batch_root_64x2p22(ml, big_oracle):
         local.append(t)
     root = sharded_batch_commit(local, n, B, CudaBackend(), None, mode="serial")
     assert root == want
+    # the C-ABI sharded prover with 8 virtual ranks on this GPU: same root through leaf-range subtrees + top levels
+    sh = ml.ShardedBatchedProver.single_process([0] * 8, B, 22)
+    assert sh.batch_commit_dev([local[j].data_ptr() for j in sh.local_polys()]) == want
+    sh.free()
     fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "batch_root_64x2p22.json")))
     assert fx["root"] == want.hex() and fx["n_polys"] == B and fx["log_n"] == 22
 
