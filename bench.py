@@ -158,42 +158,65 @@ def run_reference(args):
     return 0
 
 
-def run_batched_commit(torch, ml, L, dist, world, rank, n_polys, log_n, reps=3):
-    """BASELINE configs[4]: batched commit of n_polys polynomials of 2^log_n evaluations, sharded by polynomial for the
-    encode and by leaf range for the hashing (multilinear_b200/sharded.py).  N > 1: the exchange is the store pass
-    writing through NVLink peer mappings; the only collectives are a barrier and the 32-byte root all-gather.
-    Strong scaling (the batch is fixed); reported beside the headline metric, not as it."""
-    from multilinear_b200.sharded import CudaBackend, sharded_batch_commit
+def run_batched_commit(torch, ml, L, dist, world, rank, local_rank, n_polys, log_n, reps=3):
+    """BASELINE configs[4]: BatchedPCSProof::prove of n_polys polynomials of 2^log_n evaluations, sharded by polynomial for the
+    encode and by leaf range for hashing / fingerprints / first fold / openings (ml_shard_*, csrc/shard.cu).  One process per GPU;
+    the arenas are connected through CUDA IPC records all-gathered once over torch.distributed; on the data path the only
+    exchange is kernels storing into peer HBM over NVLink plus device-side flags (no NCCL, no host barrier).
+    Strong scaling (the batch is fixed): `ms` = commit phase (batch root, the north-star's "batched commits"), `prove_ms` = the
+    whole proof.  Reported beside the headline metric, not as it."""
+    import hashlib
+    import numpy as np
     if n_polys % world or (1 << log_n) % world:
         return None
     n = 1 << log_n
-    be = CudaBackend()
+    dev = torch.device("cuda", local_rank)
+    sh = ml.ShardedBatchedProver.one_rank(rank, world, local_rank, n_polys, log_n)
+    if world > 1:
+        sh.connect_over(dist, dev)
     mine = []
-    for j in range(rank, n_polys, world):
-        t = torch.empty(16 * n, dtype=torch.uint8, device="cuda")
+    for j in sh.local_polys():
+        t = torch.empty(16 * n, dtype=torch.uint8, device=dev)
         ml.check(L.ml_synthetic_elements_dev(C.c_uint64(5000 + j), C.c_size_t(n), C.c_void_p(t.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         mine.append(t)
-    mode = "p2p" if world > 1 else "serial"
-    launches0 = ml.kernel_launches()
-    root = sharded_batch_commit(mine, n, n_polys, be, dist, mode=mode)  # warm-up: tables, pool, peer mappings
-    per_call = ml.kernel_launches() - launches0
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        root = sharded_batch_commit(mine, n, n_polys, be, dist, mode=mode)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    if dist is not None:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
-    be.release_peer_buffers()
-    del mine
-    torch.cuda.empty_cache()
+    ptrs = [t.data_ptr() for t in mine]
+    inputs = ml.synthetic_elements_dev(0xC1A1, log_n).elems()
+    outs = np.zeros((n_polys, 16), dtype=np.uint8)
+    for j, t in zip(sh.local_polys(), mine):
+        ob = (C.c_uint8 * 16)()
+        ml.check(L.ml_mle_evals_evaluate_dev(C.c_void_p(t.data_ptr()), C.c_size_t(n), C.c_void_p(inputs.ctypes.data), C.c_size_t(log_n), ob, None))
+        outs[j] = np.frombuffer(bytes(ob), dtype=np.uint8)
+    if world > 1:
+        g = torch.from_numpy(outs).to(dev).to(torch.int32)
+        dist.all_reduce(g)  # rows are disjoint across ranks
+        outs = g.to(torch.uint8).cpu().numpy()
+    stream = torch.cuda.ExternalStream(sh.stream(0), device=dev)
+
+    def sync():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def timed(fn):
+        launches0 = ml.kernel_launches()
+        out = fn()  # warm-up: tables, pools
+        per_call = ml.kernel_launches() - launches0
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            out = fn()
+        e1.record(stream)
+        sync()
+        ms = e0.elapsed_time(e1) / reps
+        if dist is not None:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt[0])
+        return ms, out, per_call
+
+    commit_ms, root, commit_launches = timed(lambda: sh.batch_commit_dev(ptrs))
+    prove_ms, proof, prove_launches = timed(lambda: sh.prove_dev(inputs, outs, ptrs, ml.Transcript()))
     fixture_ok = None
     try:  # the oracle's root for exactly this workload (tests/golden/gen_batch_root.py)
         fx = json.load(open(os.path.join(ROOT, "tests", "golden", "batch_root_64x2p22.json")))
@@ -201,10 +224,25 @@ def run_batched_commit(torch, ml, L, dist, world, rank, n_polys, log_n, reps=3):
             fixture_ok = bool(fx["root"] == root.hex())
     except Exception:  # noqa: BLE001
         pass
-    return {"workload": "batched_commit_%dx2^%d" % (n_polys, log_n), "mode": mode, "ms": ms, "value": n_polys * n / (ms * 1e-3) / 1e6,
-            "unit": UNIT, "scaling": "strong", "root": root.hex(), "root_matches_oracle_fixture": fixture_ok,
-            "launches_per_commit_per_rank": per_call,
-            "exchange": "none" if world == 1 else "pack pass stores pairs into peer HBM over NVLink (CUDA IPC); barrier + 32-byte root all-gather over NCCL"}
+    res = {"workload": "batched_pcs_prove_%dx2^%d" % (n_polys, log_n), "api": "ml_shard_batch_commit_dev / ml_shard_batched_pcs_prove_dev",
+           "exchange": "none" if world == 1 else "kernels store into peer HBM over NVLink (CUDA IPC arenas) + device flags; no NCCL on the data path",
+           "launches_per_commit_per_rank": commit_launches, "launches_per_prove_per_rank": prove_launches,
+           "root": root.hex(), "root_matches_oracle_fixture": fixture_ok, "unit": UNIT, "scaling": "strong", "n_gpus": world}
+    if proof is not None:
+        blob = proof.fri_proof.serialize()
+        res["proof_sha256"] = hashlib.sha256(blob).hexdigest()
+        res["proof_verifies"] = proof.verify(ml.Transcript()) == 0
+    # the numbers last: the driver keeps the tail of the line
+    res["prove_ms"] = prove_ms
+    res["prove_value"] = n_polys * n / (prove_ms * 1e-3) / 1e6
+    res["ms"] = commit_ms
+    res["value"] = n_polys * n / (commit_ms * 1e-3) / 1e6
+    del proof
+    sync()
+    sh.free()
+    del mine
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_ours(args):
@@ -422,9 +460,9 @@ def run_ours(args):
         # secondary leg: never let it take the headline line down (e.g. a box without peer access between two GPUs);
         # every rank takes the same branch because the failure modes are collective (IPC mapping, NCCL)
         try:
-            batched = run_batched_commit(torch, ml, L, dist, world, rank, args.batched_polys, args.batched_log_n)
+            batched = run_batched_commit(torch, ml, L, dist, world, rank, local_rank, args.batched_polys, args.batched_log_n)
         except Exception as e:  # noqa: BLE001
-            batched = {"workload": "batched_commit_%dx2^%d" % (args.batched_polys, args.batched_log_n), "error": str(e)[:300]}
+            batched = {"workload": "batched_pcs_prove_%dx2^%d" % (args.batched_polys, args.batched_log_n), "error": str(e)[:300]}
 
     # max over ranks
     if dist is not None:
