@@ -783,3 +783,27 @@ def test_sharded_batch_commit_two_gpus_all_exchange_modes(ml):
     assert [l["mode"] for l in lines] == ["serial", "pipelined", "p2p"]
     assert all(l["matches_single_gpu"] is True and l["n_gpus"] == 2 for l in lines)
     assert len({l["root"] for l in lines}) == 1
+
+
+def test_sharded_prove_two_processes_two_gpus_vs_oracle(ml):
+    """ml_shard_* with one process per GPU (CUDA IPC arenas, NVLink stores, device flags) on two ranks: the proof equals the CPU
+    oracle's BatchedPCSProof::prove byte for byte and both transcripts end in the same state.  Skipped on a one-GPU box: ranks
+    that wait on each other must not share a GPU; the same protocol runs there as virtual ranks in lock step (tests above)."""
+    import json
+    import os
+    import socket
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tools", "sharded_prove_demo.py"), "14", "8", "oracle", "2"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    line = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{") and "sharded_batched_pcs_prove" in l][-1]
+    assert line["n_gpus"] == 2 and line["matches_oracle"] is True and line["verifies"] is True and line["transcripts_agree"] is True
