@@ -13,6 +13,7 @@
 //     3. store un-bit-reversed, fused with the inter-pass twiddle w_N^(k*b*A) (two-level table, one extra multiply);
 //        the last pass instead writes natural order k = k_0 + R_0*k_1 + ... in T-element runs.
 //   The bit-reversal permutations of the reference never touch HBM; index math is checked by tools/ntt_model.py.
+#include <cstdlib>
 #include "field.cuh"
 #include "internal.h"
 
@@ -293,6 +294,10 @@ static int get_pass_table(Ctx* ctx, int log_n, bool inverse, int pass, int log_a
     *out = nullptr;
     const size_t count = (size_t)1 << (log_r + log_b);
     if (count * 16 > ((size_t)1 << 30)) return ML_OK;
+    // MLB_NTT_NO_WTAB: experiment switch — inter-pass twiddles from the two-level root tables (one more multiply per element and
+    // pass, no N-entry matrix read from HBM); measured in profiles/r2_ntt_variants.txt
+    static const bool no_wtab = getenv("MLB_NTT_NO_WTAB") != nullptr;
+    if (no_wtab) return ML_OK;
     std::lock_guard<std::mutex> lock(ctx->roots_mu);
     RootTables& rt = ctx->roots[log_n];  // exists: get_root_tables ran first
     fe*& slot = rt.pass_tw[inverse ? 1 : 0][pass];
