@@ -119,6 +119,9 @@ int ml_intt(const uint8_t *evals, size_t n, const uint8_t gen[16], uint8_t *coef
 int ml_ntt_dev(const void *coeffs_dev, size_t n, const uint8_t gen[16], void *evals_dev, void *stream);
 int ml_intt_dev(const void *evals_dev, size_t n, const uint8_t gen[16], void *coeffs_dev, void *stream);
 int ml_poly_evaluate(const uint8_t *coeffs, size_t n, const uint8_t x[16], uint8_t out[16]); /* Polynomial::evaluate :62-67 */
+/* univariate helpers of src/polynomials.rs on the domain 0..n-1 (the sumcheck round polynomials, n <= 4 in the crate) */
+int ml_poly_interpolate(const uint8_t *evals, size_t n, uint8_t *coeffs_out);          /* PolynomialEvals::interpolate :51-86 (host scalars, n <= 2^14) */
+int ml_poly_evaluate_over_domain(const uint8_t *coeffs, size_t n, uint8_t *evals_out);  /* Polynomial::evaluate_over_domain :16-28 */
 int ml_reed_solomon(const uint8_t *coeffs, size_t n, const uint8_t gen[16], uint8_t *code /* 2n */); /* src/fri/mod.rs:19-28 */
 int ml_reed_solomon_dev(const void *coeffs_dev, size_t n, const uint8_t gen[16], void *code_dev, void *stream);
 
@@ -195,6 +198,7 @@ int ml_fri_proof_last(const ml_fri_proof *p, uint8_t last_elem[16], uint8_t last
 /* wire format of `bincode::serde::encode_to_vec(&proof, standard().with_little_endian().with_fixed_int_encoding())` (:367-391) */
 size_t ml_fri_proof_serialized_len(const ml_fri_proof *p);
 int ml_fri_proof_serialize(const ml_fri_proof *p, uint8_t *out);
+int ml_fri_proof_deserialize(const uint8_t *blob, size_t len, ml_fri_proof **out); /* a proof made elsewhere (e.g. by the Rust crate): ML_ERR_ARG if malformed */
 
 /* ---- sumcheck tables, PCS specialisation: width 1, composition |x| x[0] (src/constraint_system/sumcheck.rs:127-277) ---- */
 typedef struct ml_sumcheck ml_sumcheck;

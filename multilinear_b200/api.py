@@ -234,6 +234,33 @@ def polynomial_evaluate(coeffs, x):
 
 
 # ----------------------------------------------------------------------------- multilinear polynomials (src/polynomials.rs)
+class PolynomialEvals:
+    """src/polynomials.rs:45-86 — evaluations over the domain 0..n-1"""
+
+    def __init__(self, evals):
+        self.evals = as_elems(evals)
+
+    def interpolate(self):
+        out = elems_empty(self.evals.shape[0])
+        check(load().ml_poly_interpolate(_p(self.evals), _sz(self.evals.shape[0]), _p(out)))
+        return UnivariatePolynomial(out)
+
+
+class UnivariatePolynomial:
+    """src/polynomials.rs:3-28 (`Polynomial<F>` of that module)"""
+
+    def __init__(self, coeffs):
+        self.coeffs = as_elems(coeffs)
+
+    def evaluate(self, x):
+        return polynomial_evaluate(self.coeffs, x)
+
+    def evaluate_over_domain(self):
+        out = elems_empty(self.coeffs.shape[0])
+        check(load().ml_poly_evaluate_over_domain(_p(self.coeffs), _sz(self.coeffs.shape[0]), _p(out)))
+        return PolynomialEvals(out)
+
+
 class MultilinearPolynomialEvals:
     def __init__(self, evals):
         self.evals = as_elems(evals)
@@ -411,6 +438,14 @@ class FriProof:
         c = as_elems(coeffs)
         h = C.c_void_p()
         check(load().ml_rs_fri_prove(_p(c), _sz(c.shape[0]), transcript.h, C.byref(h)))
+        return FriProof(h)
+
+    @staticmethod
+    def deserialize(blob):
+        """a FriProof from its bincode bytes (fri/mod.rs:367-397) — e.g. one made by the Rust crate"""
+        b = np.frombuffer(bytes(blob), dtype=np.uint8).copy()
+        h = C.c_void_p()
+        check(load().ml_fri_proof_deserialize(_p(b), _sz(len(b)), C.byref(h)))
         return FriProof(h)
 
     def verify(self):

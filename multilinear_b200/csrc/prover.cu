@@ -726,6 +726,55 @@ void write_fri_proof(const ml_fri_proof* p, Writer& w) {
     w.febytes(le);
     w.bytes(p->last_random, 32);
 }
+// inverse of write_fri_proof (the crate's serde/bincode derives, fri/mod.rs:239-249): false on malformed input
+struct Reader {
+    const uint8_t* p;
+    size_t n, o = 0;
+    bool ok = true;
+    Reader(const uint8_t* b, size_t len) : p(b), n(len) {}
+    bool take(void* dst, size_t len) {
+        if (!ok || len > n - o) { ok = false; return false; }
+        memcpy(dst, p + o, len);
+        o += len;
+        return true;
+    }
+    uint64_t u64() { uint64_t v = 0; take(&v, 8); return v; }
+    uint32_t u32() { uint32_t v = 0; take(&v, 4); return v; }
+    bool febytes(uint8_t* out) { return u64() == 16 && take(out, 16); }
+};
+bool read_fri_proof(Reader& r, ml_fri_proof* p) {
+    const uint64_t nc = r.u64();
+    if (!r.ok || nc > 64) return false;
+    p->commitments.resize(32 * nc);
+    r.take(p->commitments.data(), 32 * nc);
+    const uint64_t nq = r.u64();
+    if (!r.ok || nq > 4096) return false;
+    p->queries.resize(nq);
+    for (QueryH& q : p->queries) {
+        const uint64_t np = r.u64();
+        if (!r.ok || np > 64) return false;
+        q.paths.resize(np);
+        for (PathH& ph : q.paths) {
+            ph.value.resize(32);
+            if (!r.febytes(ph.value.data()) || !r.febytes(ph.value.data() + 16)) return false;
+            const uint64_t len = r.u64();
+            if (!r.ok || len > 64) return false;
+            ph.digests.resize(32 * len);
+            ph.dirs.resize(len);
+            for (uint64_t i = 0; i < len; i++) {
+                r.take(&ph.digests[32 * i], 32);
+                const uint32_t d = r.u32();
+                if (!r.ok || d > 1) return false;
+                ph.dirs[i] = (uint8_t)d;
+            }
+        }
+    }
+    uint8_t le[16];
+    if (!r.febytes(le)) return false;
+    p->last_elem = hfe_load(le);
+    if (p->last_elem >= HFE_M) return false;
+    return r.take(p->last_random, 32);
+}
 void write_bfri_proof(const ml_bfri_proof* p, Writer& w) {
     w.bytes(p->batch_commitment, 32);
     w.u64(p->commitments.size() / 32);
@@ -1222,6 +1271,13 @@ int ml_fri_proof_last(const ml_fri_proof* p, uint8_t last_elem[16], uint8_t last
 }
 size_t ml_fri_proof_serialized_len(const ml_fri_proof* p) { Writer w(nullptr); write_fri_proof(p, w); return w.n; }
 int ml_fri_proof_serialize(const ml_fri_proof* p, uint8_t* out) { Writer w(out); write_fri_proof(p, w); return ML_OK; }
+int ml_fri_proof_deserialize(const uint8_t* blob, size_t len, ml_fri_proof** out) {
+    ml_fri_proof* p = new ml_fri_proof();
+    Reader r(blob, len);
+    if (!read_fri_proof(r, p) || r.o != len) { delete p; set_error("FriProof blob is malformed"); return ML_ERR_ARG; }
+    *out = p;
+    return ML_OK;
+}
 
 // ================================================================== sumcheck
 int ml_sumcheck_build_tables_for_pcs(const uint8_t* inputs, size_t n_vars, const uint8_t* evals, size_t height, ml_sumcheck** out) {
@@ -1444,6 +1500,55 @@ int ml_wsumcheck_compute_polynomials(ml_wsumcheck* w, size_t composition_degree,
     }
     MLB_CUDA(cudaStreamSynchronize(w->stream));
     return ML_OK;
+}
+// PolynomialEvals::interpolate (src/polynomials.rs:51-86): coefficients of the degree < n polynomial through (i, evals[i]), i = 0..n-1.
+// The reference builds every Lagrange basis polynomial with poly_mul (O(n^3)); the interpolant is unique, so the same coefficients come
+// from the master polynomial P(x) = prod (x - m) divided synthetically by (x - j), O(n^2).  Host scalars: the reference only calls it
+// with n = total_degree + 1 <= 4 (sumcheck.rs:189-192).
+int ml_poly_interpolate(const uint8_t* evals, size_t n, uint8_t* coeffs_out) {
+    if (n == 0) return ML_OK;
+    if (n > ((size_t)1 << 14)) { set_error("interpolate: at most 2^14 points (host scalar routine)"); return ML_ERR_ARG; }
+    std::vector<hfe> P(n + 1, 0), q(n), c(n, 0), fact(n, 1);
+    P[0] = 1;  // P(x) = prod_{m<n} (x - m), ascending coefficients
+    for (size_t m = 0; m < n; m++) {
+        const hfe xm = hfe_new((hfe)m);
+        for (size_t i = m + 1; i-- > 0;) P[i + 1] = hfe_add(P[i + 1], P[i]), P[i] = hfe_neg(hfe_mul(P[i], xm));
+    }
+    for (size_t i = 1; i < n; i++) fact[i] = hfe_mul(fact[i - 1], hfe_new((hfe)i));
+    for (size_t j = 0; j < n; j++) {
+        const hfe xj = hfe_new((hfe)j);
+        // q = P / (x - j): q[n-1] = P[n], q[i-1] = P[i] + j * q[i]
+        q[n - 1] = P[n];
+        for (size_t i = n - 1; i >= 1; i--) q[i - 1] = hfe_add(P[i], hfe_mul(xj, q[i]));
+        // denom = prod_{m != j} (j - m) = j! * (n-1-j)! * (-1)^(n-1-j)
+        hfe denom = hfe_mul(fact[j], fact[n - 1 - j]);
+        if ((n - 1 - j) & 1) denom = hfe_neg(denom);
+        const hfe scale = hfe_div(hfe_load(evals + 16 * j), denom);
+        for (size_t i = 0; i < n; i++) c[i] = hfe_add(c[i], hfe_mul(scale, q[i]));
+    }
+    for (size_t i = 0; i < n; i++) hfe_store(coeffs_out + 16 * i, c[i]);
+    return ML_OK;
+}
+// Polynomial::evaluate_over_domain (src/polynomials.rs:16-28): evals[i] = p(i), i = 0..n-1; one thread per point, Horner
+__global__ void poly_eval_domain_kernel(const fe* __restrict__ coeffs, size_t n, fe* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fe x = fe{{(uint32_t)i, (uint32_t)(i >> 32), 0u, 0u}};
+    fe acc = fe_zero();
+    for (size_t k = n; k-- > 0;) acc = fe_add(fe_mul(acc, x), fe_load_nc(coeffs + k));
+    fe_store(out + i, acc);
+}
+int ml_poly_evaluate_over_domain(const uint8_t* coeffs, size_t n, uint8_t* evals_out) {
+    API_BEGIN
+    if (n == 0) return ML_OK;
+    cudaStream_t s = lib_stream(ctx);
+    Scratch dc(s), de(s);
+    MLB_TRY(dc.alloc(n * 16));
+    MLB_TRY(de.alloc(n * 16));
+    MLB_TRY(h2d(dc.p, coeffs, n * 16, s));
+    poly_eval_domain_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(dc.as<fe>(), n, de.as<fe>());
+    MLB_KERNEL_CHECK();
+    return d2h_sync(evals_out, de.p, n * 16, s);
 }
 int ml_delta_evaluate(const uint8_t* data, const uint8_t* points, size_t n, uint8_t out[16]) {
     std::vector<hfe> a(n), b(n);

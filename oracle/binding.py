@@ -149,6 +149,11 @@ class Oracle:
         assert st == 0, st
         return out
 
+    def interpolate(self, evals):
+        out = elems_empty(evals.shape[0])
+        self.L.or_interpolate(buf(evals), sz(evals.shape[0]), buf(out))
+        return out
+
     def bit_reverse(self, a):
         a = np.ascontiguousarray(a).copy()
         self.L.or_bit_reverse_permutation(buf(a), sz(a.shape[0]), sz(a.shape[1]))

@@ -266,6 +266,77 @@ def test_fri_prove_vs_oracle_and_errors(ml, oracle):
         ml.FriProof.prove(code, gp[:100], ml.Transcript())
 
 
+def test_fri_verifier_rejects_tampered_proofs(ml, oracle):
+    """every FriProofError of the reference's verifier (src/fri/mod.rs:251-258, 287-340) is reachable through the C ABI:
+    a proof is serialised, one field is changed, and the re-read proof must fail with the matching ML_V_* code"""
+    from multilinear_b200._lib import MlError
+    log_n = 9
+    coeffs = oracle.synthetic(41, 1 << log_n)
+    proof = ml.FriProof.prove_from_coeffs(coeffs, ml.Transcript())
+    blob = bytearray(proof.serialize())
+    assert ml.FriProof.deserialize(blob).verify() == 0 and ml.FriProof.deserialize(blob).serialize() == bytes(blob)
+    nc = int.from_bytes(blob[0:8], "little")
+    assert nc == log_n
+    q0 = 8 + 32 * nc + 8                       # first query: u64 path count, then per path: pair (2 x 24 B), u64 len, len x 36 B
+    sizes = []
+    off = q0 + 8
+    for j in range(nc):
+        ln = int.from_bytes(blob[off + 48:off + 56], "little")
+        sizes.append(56 + 36 * ln)
+        off += sizes[-1]
+    qlen = off - q0                            # all 128 queries have the same byte length
+    # ML_V_INCLUSION_HASH (104): one byte of a sibling digest on the first path of the first query
+    b = bytearray(blob); b[q0 + 8 + 56 + 5] ^= 1
+    assert ml.FriProof.deserialize(b).verify() == 104
+    # ... or of an opened value
+    b = bytearray(blob); b[q0 + 8 + 8 + 3] ^= 1
+    assert ml.FriProof.deserialize(b).verify() == 104
+    # ML_V_INCLUSION_INDEX (105): two valid openings swapped — the hashes match their roots, the transcript asks for other indices
+    b = bytearray(blob)
+    a0, a1 = bytes(b[q0:q0 + qlen]), bytes(b[q0 + qlen:q0 + 2 * qlen])
+    if a0 != a1:
+        b[q0:q0 + qlen], b[q0 + qlen:q0 + 2 * qlen] = a1, a0
+        assert ml.FriProof.deserialize(b).verify() == 105
+    # ML_V_LAST_RANDOM (106): the recorded final transcript state
+    b = bytearray(blob); b[-1] ^= 0x80
+    assert ml.FriProof.deserialize(b).verify() == 106
+    # a different last element: it is absorbed before the indices are drawn, so the openings no longer match the indices asked
+    # for (105), or — should an index survive — the fold consistency check (101)
+    b = bytearray(blob); b[-32 - 16] ^= 1
+    assert ml.FriProof.deserialize(b).verify() in (101, 105)
+    # a changed commitment changes every later challenge: rejected (which check fires first depends on the layer)
+    b = bytearray(blob); b[8 + 32 * 2 + 7] ^= 1
+    assert ml.FriProof.deserialize(b).verify() in (101, 104, 105)
+    # ML_V_WRONG_NUM_PATHS (103): the commitment list is one short of the paths
+    b = bytearray(blob[:8 + 32 * (nc - 1)] + blob[8 + 32 * nc:]); b[0:8] = (nc - 1).to_bytes(8, "little")
+    assert ml.FriProof.deserialize(b).verify() == 103
+    # ML_V_WRONG_NUM_QUERIES (102): 127 queries
+    b = bytearray(blob[:q0 - 8] + (127).to_bytes(8, "little") + blob[q0 + qlen:])
+    assert ml.FriProof.deserialize(b).verify() == 102
+    with pytest.raises(MlError):
+        ml.FriProof.deserialize(blob[:-3])     # truncated blob
+    with pytest.raises(MlError):
+        ml.FriProof.deserialize(bytes(blob) + b"\x00")
+
+
+def test_univariate_interpolation_reference_test(ml, oracle):
+    """interpolation_test (src/polynomials.rs:197-204) and PolynomialEvals::interpolate against the oracle"""
+    evals = ml.PolynomialEvals(ml.from_i64([0, 1, 4, 8, 9, 3]))
+    pol = evals.interpolate()
+    assert np.array_equal(pol.evaluate_over_domain().evals, evals.evals)
+    assert np.array_equal(pol.coeffs, oracle.interpolate(evals.evals))
+    for n in (1, 2, 3, 4, 17, 64):
+        e = oracle.synthetic(600 + n, n)
+        c = ml.PolynomialEvals(e).interpolate()
+        assert np.array_equal(c.coeffs, oracle.interpolate(e)), n
+        assert np.array_equal(c.evaluate_over_domain().evals, e)
+        assert c.evaluate(n - 1) == fe_ints(e)[n - 1]
+    big = oracle.synthetic(5, 3000)
+    got = ml.UnivariatePolynomial(big).evaluate_over_domain().evals
+    for i in (0, 1, 2999):
+        assert fe_ints(got[i:i + 1])[0] == P.poly_eval(fe_ints(big), i)
+
+
 # ------------------------------------------------------------------ sumcheck
 @pytest.mark.parametrize("nv", [1, 2, 5, 12, 13, 16])
 def test_sumcheck_tables_and_rounds(ml, oracle, nv):
