@@ -93,6 +93,10 @@ int ml_dev_upload(void *dst_dev, const void *src_host, size_t bytes);
 int ml_dev_download(void *dst_host, const void *src_dev, size_t bytes);
 int ml_host_alloc_pinned(size_t bytes, void **out);
 int ml_host_free_pinned(void *p);
+/* page-lock / unlock memory the caller allocated itself (Vec<Field128>, numpy array), so host-pointer entry points upload from it
+ * at pinned-memory speed; unregister before freeing it.  Unregistered (pageable) inputs work too, through the driver's staging copies. */
+int ml_host_register(void *p, size_t bytes);
+int ml_host_unregister(void *p);
 
 /* ---- field (src/field.rs:66-154; winter-math f128).  Element-wise vector ops run on the GPU. ---- */
 int ml_fe_add_vec(const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out);

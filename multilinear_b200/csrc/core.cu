@@ -312,6 +312,10 @@ int ml_dev_upload(void* dst, const void* src, size_t bytes) { MLB_CUDA(cudaMemcp
 int ml_dev_download(void* dst, const void* src, size_t bytes) { MLB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return ML_OK; }
 int ml_host_alloc_pinned(size_t bytes, void** out) { MLB_CUDA(cudaMallocHost(out, bytes ? bytes : 16)); return ML_OK; }
 int ml_host_free_pinned(void* p) { MLB_CUDA(cudaFreeHost(p)); return ML_OK; }
+// page-lock memory the caller allocated itself (a Vec<Field128>, a numpy array): uploads from it then run at pinned-memory speed.
+// The caller must unregister before freeing the memory.
+int ml_host_register(void* p, size_t bytes) { MLB_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterDefault)); return ML_OK; }
+int ml_host_unregister(void* p) { MLB_CUDA(cudaHostUnregister(p)); return ML_OK; }
 
 // ------------------------------------------------------------------ helpers for host-pointer entry points
 static int upload(Scratch& sc, const void* host, size_t bytes, cudaStream_t s) {

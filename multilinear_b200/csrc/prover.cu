@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <thread>
 #include "prover_internal.h"
 
 using namespace mlb;
@@ -51,6 +52,59 @@ static void trace_dump_impl() {
 // 16 MB and more (documented in include/multilinear_b200.h).
 static const int MAX_UPLOAD_DEVICES = 64;
 static std::mutex g_upload_mu[MAX_UPLOAD_DEVICES];
+// Pageable host memory (a plain Vec<Field128> / malloc / numpy array the caller never page-locked): cudaMemcpyAsync stages it through
+// the driver's own bounce buffer on ONE thread, 11.5 GB/s on the bench box against 55 GB/s from pinned memory, and page-locking it
+// in place costs more than the copy (cudaHostRegister 45 ms + unregister 17 ms for 256 MiB; tools/h2d_probe.py).  So the library
+// stages it itself: STAGE_THREADS host threads copy 4 MiB chunks into a per-device ring of pinned slots (two per thread) and
+// queue the DMA of each slot on the caller's stream; the host copies of different threads and the DMA overlap.
+static const size_t STAGE_CHUNK = (size_t)4 << 20;
+static const int STAGE_THREADS = 4, STAGE_SLOTS = 2 * STAGE_THREADS;
+struct Stager {
+    uint8_t* slot[STAGE_SLOTS] = {nullptr};
+    cudaEvent_t ev[STAGE_SLOTS] = {nullptr};
+    bool ready = false, failed = false;
+};
+static Stager g_stager[MAX_UPLOAD_DEVICES];  // used under g_upload_mu[dev]
+static bool stager_init(Stager& st) {
+    if (st.ready || st.failed) return st.ready;
+    for (int i = 0; i < STAGE_SLOTS; i++)
+        if (cudaMallocHost((void**)&st.slot[i], STAGE_CHUNK) != cudaSuccess || cudaEventCreateWithFlags(&st.ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            st.failed = true;  // fall back to the driver's staging for good
+            return false;
+        }
+    st.ready = true;
+    return true;
+}
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+static int staged_upload(void* dst, const void* src, size_t bytes, cudaStream_t s, int dev, Stager& st) {
+    const size_t n_chunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    std::atomic<size_t> next{0};
+    std::atomic<int> status{ML_OK};
+    auto work = [&](int w) {
+        if (cudaSetDevice(dev) != cudaSuccess) { status = ML_ERR_CUDA; return; }
+        for (size_t k = 0;; k++) {
+            const size_t c = next.fetch_add(1);
+            if (c >= n_chunks || status != ML_OK) return;
+            const int sl = 2 * w + (int)(k & 1);
+            if (k >= 2 && cudaEventSynchronize(st.ev[sl]) != cudaSuccess) { status = ML_ERR_CUDA; return; }  // the slot's previous DMA is done
+            const size_t off = c * STAGE_CHUNK, len = bytes - off < STAGE_CHUNK ? bytes - off : STAGE_CHUNK;
+            memcpy(st.slot[sl], (const uint8_t*)src + off, len);
+            if (cudaMemcpyAsync((uint8_t*)dst + off, st.slot[sl], len, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+                cudaEventRecord(st.ev[sl], s) != cudaSuccess) { status = ML_ERR_CUDA; return; }
+        }
+    };
+    std::thread th[STAGE_THREADS - 1];
+    for (int w = 1; w < STAGE_THREADS; w++) th[w - 1] = std::thread(work, w);
+    work(0);
+    for (auto& t : th) t.join();
+    if (status != ML_OK) { set_error("staged upload failed: %s", cudaGetErrorString(cudaGetLastError())); return status; }
+    return ML_OK;
+}
 int h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
     if (!bytes) return ML_OK;
     if (bytes < ((size_t)16 << 20)) {
@@ -63,7 +117,10 @@ int h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
     trace("upload_wait");
     std::lock_guard<std::mutex> lock(g_upload_mu[dev % MAX_UPLOAD_DEVICES]);
     trace("upload_begin");
-    MLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    static const bool no_stage = getenv("MLB_NO_STAGED_UPLOAD") != nullptr;
+    Stager& stg = g_stager[dev % MAX_UPLOAD_DEVICES];
+    if (!no_stage && is_pageable(src) && stager_init(stg)) MLB_TRY(staged_upload(dst, src, bytes, s, dev, stg));
+    else MLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
     int st = stream_wait_blocking(s);  // the stream holds nothing but the copy now
     trace("upload_done");
     return st;
