@@ -245,6 +245,101 @@ def run_batched_commit(torch, ml, L, dist, world, rank, local_rank, n_polys, log
     return res
 
 
+def run_other_configs(torch, ml, L, threads):
+    """BASELINE configs[0], [1], [3] beside the headline (configs[2]): three numbers each — device-resident rate (CUDA events),
+    end-to-end rate through the host-pointer C ABI (wall clock, copies included), the CPU oracle on all host threads — and a
+    bit-exact comparison of the CUDA result with the oracle's on the same inputs."""
+    import numpy as np
+    from oracle.binding import Oracle
+    O = Oracle(threads=threads)
+    out = {}
+
+    def gpu_ms(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def wall_ms(fn, reps=3):
+        fn()
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            r = fn()
+            dt = (time.perf_counter() - t0) * 1e3
+            best = dt if best is None or dt < best else best
+        return best, r
+
+    def rate(n, ms):
+        return n / (ms * 1e-3) / 1e6
+
+    # ---- configs[1]: forward + inverse NTT, one polynomial of 2^20 coefficients, blowup 2
+    n = 1 << 20
+    hc = O.synthetic(0xB200, n)
+    g21 = ml.pow_2_generator(21)
+    gb = (C.c_uint8 * 16)(*g21.to_bytes(16, "little"))
+    dc, dcode, dback = ml.DeviceBuffer.from_host(hc), ml.DeviceBuffer(32 * n), ml.DeviceBuffer(32 * n)
+
+    def ntt_dev():
+        ml.check(L.ml_reed_solomon_dev(dc.ptr, C.c_size_t(n), gb, dcode.ptr, None))
+        ml.check(L.ml_intt_dev(dcode.ptr, C.c_size_t(2 * n), gb, dback.ptr, None))
+
+    d_ms = gpu_ms(ntt_dev, reps=10)
+    e_ms, (code, back) = wall_ms(lambda: (lambda c: (c, ml.intt(c, g21)))(ml.reed_solomon(hc, g21)))
+    t0 = time.perf_counter()
+    ocode = O.reed_solomon(hc, g21)
+    oback = O.intt(ocode, g21)
+    c_ms = (time.perf_counter() - t0) * 1e3
+    out["ntt_2p20_blowup2_fwd_inv"] = {"value": rate(n, d_ms), "e2e": rate(n, e_ms), "cpu": rate(n, c_ms), "unit": UNIT, "device_ms": d_ms,
+                                       "bit_exact": bool(np.array_equal(code, ocode) and np.array_equal(back, oback))}
+    del dc, dcode, dback
+
+    # ---- configs[3]: sumcheck over a 2^24-entry multilinear extension product, all rounds
+    nv = 24
+    n = 1 << nv
+    ev = O.synthetic(0xB200, n)
+    inp = O.synthetic(0xB2000001, nv)
+    claim = O.mle_evals_evaluate(ev, inp)
+    dev = ml.DeviceBuffer.from_host(ev)
+
+    def sc_dev():
+        h = C.c_void_p()
+        ml.check(L.ml_sumcheck_build_tables_for_pcs_dev(C.c_void_p(inp.ctypes.data), C.c_size_t(nv), dev.ptr, C.c_size_t(n), None, C.byref(h)))
+        return ml.SumcheckTables(h).compute_sumcheck_polynomials(1, ml.Transcript(), claim)
+
+    d_ms = gpu_ms(sc_dev)
+    e_ms, got = wall_ms(lambda: ml.SumcheckTables.build_tables_for_pcs(inp, ev).compute_sumcheck_polynomials(1, ml.Transcript(), claim), reps=2)
+    t0 = time.perf_counter()
+    want = O.sumcheck_build(inp, ev).compute_sumcheck_polynomials(1, O.transcript(), claim)
+    c_ms = (time.perf_counter() - t0) * 1e3
+    out["sumcheck_2p24_all_rounds"] = {"value": rate(n, d_ms), "e2e": rate(n, e_ms), "cpu": rate(n, c_ms), "unit": UNIT, "device_ms": d_ms,
+                                       "bit_exact": bool(got == want)}
+    del dev
+
+    # ---- configs[0]: the reference's own end-to-end example (multilinear_pcs_bench_test: n_vars 20, evals 7i+3, inputs i)
+    nv = 20
+    n = 1 << nv
+    ev1 = ml.from_i64([7 * i + 3 for i in range(n)])
+    in1 = ml.from_i64(range(nv))
+    out1 = ml.MultilinearPolynomialEvals(ev1).evaluate(ml.to_ints(in1))
+    d1 = ml.DeviceBuffer.from_host(ev1)
+    d_ms = gpu_ms(lambda: ml.PCSProof.prove_dev(in1, out1, d1, n, ml.Transcript(), None))
+    e_ms, proof = wall_ms(lambda: ml.PCSProof.prove(in1, out1, ev1, ml.Transcript()))
+    t0 = time.perf_counter()
+    op, st = O.pcs_prove(in1, out1, ev1, O.transcript())
+    c_ms = (time.perf_counter() - t0) * 1e3
+    out["pcs_prove_reference_example_nvars20"] = {"value": rate(n, d_ms), "e2e": rate(n, e_ms), "cpu": rate(n, c_ms), "unit": UNIT, "device_ms": d_ms,
+                                                  "bit_exact": bool(st == 0 and proof.fri_proof.serialize() == op.fri.blob)}
+    out["cpu_threads"] = threads
+    return out
+
+
 def run_ours(args):
     import torch
     from multilinear_b200 import api as ml
@@ -548,6 +643,7 @@ def run_ours(args):
             extra["int_pipe_error"] = str(e)
 
         cpu_baseline = None
+        other_configs = None
         parity_at_size, parity_detail = None, None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import binding
@@ -567,6 +663,10 @@ def run_ours(args):
                 ff = ml.FriProverData.fold_from_coeffs_dev(ml.synthetic_elements_dev(0xB200, 1 << log_s), 1 << log_s, tt, streams[0].value)
                 g_roots, g_last, g_tr = ff.fold_roots(), ff.last_element, tt.random()
                 del ff
+            try:
+                other_configs = run_other_configs(torch, ml, L, threads)
+            except Exception as e:  # noqa: BLE001
+                other_configs = {"error": str(e)[:300]}
             parity_at_size = bool(g_roots == kept["roots"] and g_last == kept["last"] and g_tr == kept["transcript"])
             parity_detail = {"log_n": log_s, "seed": "0xB200", "roots_compared": len(kept["roots"]), "last_element": g_last == kept["last"],
                              "transcript": g_tr == kept["transcript"], "checker": "oracle/oracle.c (CPU restatement; unpinned against the Rust crate)"}
@@ -590,6 +690,8 @@ def run_ours(args):
                                        "4 MiB pinned slots"}},
             "gpu_launches": launches, "clocks": sampler.result(), "kernels": kernels,
         }
+        if other_configs is not None:
+            line["e2e"]["other_configs"] = other_configs
         if parity_at_size is not None:
             if roofline is not None:  # driver-preserved key (config must stay identical to the reference arm's)
                 roofline["parity_at_size"] = parity_at_size
