@@ -297,6 +297,129 @@ int chain_sumcheck_tail_launch(fe* m, fe* d, size_t height, fe* prev, DevTranscr
     return ML_OK;
 }
 
+// ------------------------------------------------------------------ width-w sumcheck rounds (sumcheck.rs:174-202) on the device
+// thread 0: evals[1..td] (sums over CTAs or over the block) -> evals[0] = prev - evals[1] (:188) -> coefficients through the
+// precomputed Lagrange matrix over x = 0..td (interpolate, :189-192) -> absorb coeffs[1..] (:193-197) -> r (:198) -> prev = p(r) (:199)
+__device__ __forceinline__ fe wchain_round_tail(const fe* ev /* td values, points 1..td */, int td, const fe* __restrict__ lag, fe prev,
+                                                DevTranscript* t, fe* coef_out, fe* prev_out) {
+    fe y[W_MAX_TD + 1], c[W_MAX_TD + 1];
+    y[0] = fe_sub(prev, ev[0]);
+    for (int k = 0; k < td; k++) y[k + 1] = ev[k];
+    const int n = td + 1;
+    for (int i = 0; i < n; i++) {
+        fe acc = fe_zero();
+        for (int j = 0; j < n; j++) acc = fe_add(acc, fe_mul(fe_load(lag + i * n + j), y[j]));
+        c[i] = acc;
+    }
+    for (int i = 1; i < n; i++) { dt_absorb_fe(t, c[i]); fe_store(coef_out + (i - 1), c[i]); }
+    const fe r = dt_challenge(t);
+    fe acc = c[n - 1];
+    for (int i = n - 2; i >= 0; i--) acc = fe_add(fe_mul(acc, r), c[i]);
+    *prev_out = acc;
+    return r;
+}
+__global__ void __launch_bounds__(256) wchain_finish_kernel(const fe* __restrict__ partials, int nb, int td, const fe* __restrict__ lag, fe* prev,
+                                                            DevTranscript* tr, fe* coef_out, fe* r_store, fe* r_dev) {
+    __shared__ fe scratch[32];
+    __shared__ fe ev[W_MAX_TD];
+    for (int k = 0; k < td; k++) {
+        fe a = fe_zero();
+        for (int b = threadIdx.x; b < nb; b += blockDim.x) a = fe_add(a, partials[(size_t)b * td + k]);
+        a = block_sum(a, scratch);
+        if (threadIdx.x == 0) ev[k] = a;
+    }
+    if (threadIdx.x != 0) return;
+    DevTranscript t = *tr;
+    fe np;
+    const fe r = wchain_round_tail(ev, td, lag, fe_load(prev), &t, coef_out, &np);
+    fe_store(prev, np);
+    fe_store(r_store, r);
+    fe_store(r_dev, r);
+    *tr = t;
+}
+// every remaining round of small width-w tables in one CTA: points 1..td in one pass per round (row_{r+1} = row_r + (x1 - x0)),
+// round bookkeeping on thread 0, fold, repeat
+__global__ void __launch_bounds__(512, 1) wchain_tail_kernel(fe* m, fe* d, size_t height, int width, WTerms terms, int td, const fe* __restrict__ lag,
+                                                              fe* prev, DevTranscript* trp, fe* coef_out, fe* rs_out) {
+    __shared__ DevTranscript tr;
+    __shared__ fe sh_r, sh_prev, scratch[32], ev[W_MAX_TD];
+    __shared__ fe t_coef[W_MAX_TERMS];
+    __shared__ uint32_t t_len[W_MAX_TERMS], t_off[W_MAX_TERMS], t_cols[W_MAX_COLS];
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    for (int t = tid; t < terms.n_terms; t += nthreads) { t_coef[t] = terms.coef[t]; t_len[t] = terms.len[t]; t_off[t] = terms.off[t]; }
+    for (int c = tid; c < terms.n_cols; c += nthreads) t_cols[c] = terms.cols[c];
+    if (tid == 0) { tr = *trp; sh_prev = fe_load(prev); }
+    __syncthreads();
+    int round = 0;
+    for (size_t h = height; h > 1; h >>= 1, round++) {
+        const size_t off = h >> 1;
+        fe_acc a[W_MAX_TD];
+        for (int k = 0; k < W_MAX_TD; k++) acc_zero(a[k]);
+        for (size_t i = tid; i < off; i += nthreads) {
+            fe row[W_MAX_WIDTH], diff[W_MAX_WIDTH];
+            for (int j = 0; j < width; j++) {
+                fe x0 = fe_load(m + i * width + j), x1 = fe_load(m + (i + off) * width + j);
+                row[j] = x1;
+                diff[j] = fe_sub(x1, x0);
+            }
+            fe d0 = fe_load(d + i), dd = fe_load(d + i + off);
+            const fe ddiff = fe_sub(dd, d0);
+            for (int k = 0; k < td; k++) {
+                fe comp = fe_zero();
+                for (int t = 0; t < terms.n_terms; t++) {
+                    fe p = t_coef[t];
+                    for (uint32_t c = 0; c < t_len[t]; c++) p = fe_mul(p, row[t_cols[t_off[t] + c]]);
+                    comp = fe_add(comp, p);
+                }
+                acc_mul_add(a[k], comp, dd);
+                if (k + 1 < td) {
+                    for (int j = 0; j < width; j++) row[j] = fe_add(row[j], diff[j]);
+                    dd = fe_add(dd, ddiff);
+                }
+            }
+        }
+        for (int k = 0; k < td; k++) {
+            fe sk = block_sum(acc_reduce(a[k]), scratch);
+            if (tid == 0) ev[k] = sk;
+        }
+        if (tid == 0) {
+            fe np;
+            const fe r = wchain_round_tail(ev, td, lag, sh_prev, &tr, coef_out + (size_t)round * td, &np);
+            sh_prev = np;
+            sh_r = r;
+            fe_store(rs_out + round, r);
+        }
+        __syncthreads();
+        const fe r = sh_r;
+        // fold (:234-247): rows i < off of the matrix and of delta
+        const size_t total = off * (size_t)(width + 1);
+        for (size_t e = tid; e < total; e += nthreads) {
+            fe* base;
+            size_t idx, hi;
+            if (e < off * (size_t)width) { base = m; idx = e; hi = e + off * (size_t)width; }
+            else { base = d; idx = e - off * (size_t)width; hi = idx + off; }
+            fe x0 = fe_load(base + idx), x1 = fe_load(base + hi);
+            fe_store(base + idx, fe_add(x0, fe_mul(r, fe_sub(x1, x0))));
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { *trp = tr; fe_store(prev, sh_prev); }
+}
+int wchain_finish_launch(const fe* partials, int nb, int td, const fe* lag, fe* prev, DevTranscript* tr, fe* coef_out, fe* r_store, fe* r_dev,
+                         cudaStream_t s) {
+    ProfScope prof(PROF_TRANSCRIPT, 0.0, s);
+    wchain_finish_kernel<<<1, 256, 0, s>>>(partials, nb, td, lag, prev, tr, coef_out, r_store, r_dev);
+    MLB_KERNEL_CHECK();
+    return ML_OK;
+}
+int wchain_tail_launch(fe* m, fe* d, size_t height, int width, const WTerms& t, int td, const fe* lag, fe* prev, DevTranscript* tr, fe* coef_out,
+                       fe* rs_out, cudaStream_t s) {
+    ProfScope prof(PROF_TAIL, 0.0, s);
+    wchain_tail_kernel<<<1, 512, 0, s>>>(m, d, height, width, t, td, lag, prev, tr, coef_out, rs_out);
+    MLB_KERNEL_CHECK();
+    return ML_OK;
+}
+
 int chain_challenge_launch(DevTranscript* tr, const uint8_t* absorb, int absorb_len, uint8_t* copy_out, fe* r_out, bool want_challenge,
                            cudaStream_t s) {
     ProfScope prof(PROF_TRANSCRIPT, 0.0, s);

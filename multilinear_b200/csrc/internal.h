@@ -186,6 +186,19 @@ int wsumcheck_partial_sum_launch(const fe* m, const fe* d, size_t height, size_t
 int wsumcheck_fold_launch(fe* m, fe* d, size_t height, size_t width, hfe r, cudaStream_t s);
 int wsumcheck_points_launch(const fe* m, const fe* d, size_t height, size_t width, const fe* coef, const uint32_t* len, const uint32_t* off,
                             const uint32_t* cols, size_t n_terms, size_t n_cols, int td, hfe* evals_out, cudaStream_t s);
+// width-w composition as a sparse polynomial over the row (device arrays): comp(x) = sum_t coef[t] * prod_{k < len[t]} x[cols[off[t] + k]]
+struct WTerms {
+    const fe* coef;
+    const uint32_t* len;
+    const uint32_t* off;
+    const uint32_t* cols;
+    int n_terms, n_cols;
+};
+static const int W_MAX_WIDTH = 16, W_MAX_TERMS = 64, W_MAX_COLS = 256, W_MAX_TD = 4;
+// device-chain pieces of the width-w sumcheck: per-CTA partials of all td points (td per CTA), fold with the challenge in HBM
+int wsumcheck_points_partials_launch(const fe* m, const fe* d, size_t height, size_t width, const WTerms& t, int td, fe* partials, int* n_blocks,
+                                     cudaStream_t s);
+int wsumcheck_fold_dev_launch(fe* m, fe* d, size_t height, size_t width, const fe* r_dev, cudaStream_t s);
 int sumcheck_fold_sums_launch(fe* m, fe* d, size_t height, const fe* r_dev, fe* partials /* 2 per CTA */, int* n_blocks, cudaStream_t s);
 int sumcheck_sums_partials_launch(const fe* m, const fe* d, size_t height, fe* partials /* 2 per CTA */, int* n_blocks, cudaStream_t s);
 int sumcheck_max_blocks();
@@ -219,5 +232,11 @@ int chain_sumcheck_finish_launch(const fe* partials, int nb, fe* prev, DevTransc
 int chain_tail_launch(const TailArgs& a, cudaStream_t s);
 int chain_sumcheck_tail_launch(fe* m, fe* d, size_t height, fe* prev, DevTranscript* tr, fe* sc_out, fe* r_out, cudaStream_t s);
 int chain_last_launch(const fe* two, DevTranscript* tr, fe* last_out, int* status, cudaStream_t s);
+// width-w sumcheck rounds on the device (sumcheck.rs:174-202): lag = the (td+1) x (td+1) Lagrange coefficient matrix over x = 0..td
+static const int WTAIL_LOG = 12;  // the tail kernel runs every remaining round once the tables have <= 2^WTAIL_LOG rows
+int wchain_finish_launch(const fe* partials, int nb, int td, const fe* lag, fe* prev, DevTranscript* tr, fe* coef_out, fe* r_store, fe* r_dev,
+                         cudaStream_t s);
+int wchain_tail_launch(fe* m, fe* d, size_t height, int width, const WTerms& t, int td, const fe* lag, fe* prev, DevTranscript* tr, fe* coef_out,
+                       fe* rs_out, cudaStream_t s);
 
 }  // namespace mlb

@@ -1536,6 +1536,53 @@ int ml_wsumcheck_compute_polynomials(ml_wsumcheck* w, size_t composition_degree,
     const size_t td = composition_degree + 1;  // :159
     if (td > 16) { set_error("composition_degree too large"); return ML_ERR_ARG; }
     const size_t rounds = w->height ? ilog2(w->height) : 0;
+    static const bool host_rounds = getenv("MLB_WSUMCHECK_HOST_ROUNDS") != nullptr;  // the round-1 path, kept for comparison
+    if (td <= (size_t)W_MAX_TD && rounds > 0 && !host_rounds) {
+        // every round on the device: points kernel -> one-CTA bookkeeping (Lagrange matrix, transcript in HBM, challenge) -> fold
+        // reading the challenge from HBM; the last WTAIL_LOG rounds in one CTA; one synchronisation at the end
+        cudaStream_t s = w->stream;
+        const size_t n = td + 1;
+        // Lagrange coefficient matrix over x = 0..td: lag[i][j] = coefficient of x^i in L_j (polynomials.rs:51-86 for unit vectors)
+        std::vector<uint8_t> lag_h(n * n * 16), unit(n * 16), col(n * 16);
+        for (size_t j = 0; j < n; j++) {
+            std::fill(unit.begin(), unit.end(), 0);
+            unit[16 * j] = 1;
+            MLB_TRY(ml_poly_interpolate(unit.data(), n, col.data()));
+            for (size_t i = 0; i < n; i++) memcpy(&lag_h[(i * n + j) * 16], &col[16 * i], 16);
+        }
+        const int max_nb = sumcheck_max_blocks();
+        Scratch blk(s);
+        const size_t off_tr = 0, off_r = 128, off_prev = 144, off_lag = 160, off_co = off_lag + 32 * 16, off_rs = off_co + 64 * W_MAX_TD * 16,
+                     off_part = off_rs + 64 * 16, total = off_part + ((size_t)max_nb + 1) * W_MAX_TD * 16;
+        MLB_TRY(blk.alloc(total));
+        uint8_t* base = blk.as<uint8_t>();
+        DevTranscript* tr_dev = (DevTranscript*)(base + off_tr);
+        fe *r_dev = (fe*)(base + off_r), *prev_dev = (fe*)(base + off_prev), *lag_dev = (fe*)(base + off_lag), *co_dev = (fe*)(base + off_co),
+           *rs_dev = (fe*)(base + off_rs), *partials = (fe*)(base + off_part);
+        MLB_TRY(h2d(tr_dev, &t->sha, sizeof(DevTranscript), s));
+        MLB_TRY(h2d(prev_dev, sum, 16, s));
+        MLB_TRY(h2d(lag_dev, lag_h.data(), lag_h.size(), s));
+        const WTerms terms{w->coef, w->len, w->off, w->cols, (int)w->n_terms, (int)w->n_cols};
+        size_t k = 0;
+        for (; k < rounds && w->height > ((size_t)1 << WTAIL_LOG); k++) {
+            int nb = 0;
+            MLB_TRY(wsumcheck_points_partials_launch(w->matrix, w->delta, w->height, w->width, terms, (int)td, partials, &nb, s));
+            MLB_TRY(wchain_finish_launch(partials, nb, (int)td, lag_dev, prev_dev, tr_dev, co_dev + k * td, rs_dev + k, r_dev, s));
+            MLB_TRY(wsumcheck_fold_dev_launch(w->matrix, w->delta, w->height, w->width, r_dev, s));
+            w->height >>= 1;
+        }
+        if (k < rounds) {
+            MLB_TRY(wchain_tail_launch(w->matrix, w->delta, w->height, (int)w->width, terms, (int)td, lag_dev, prev_dev, tr_dev, co_dev + k * td,
+                                       rs_dev + k, s));
+            w->height = 1;
+        }
+        std::vector<uint8_t> host(off_part);
+        MLB_TRY(d2h_sync(host.data(), base, off_part, s));  // also keeps lag_h alive until its upload has run
+        memcpy(coeffs_out, host.data() + off_co, rounds * td * 16);
+        memcpy(randoms_out, host.data() + off_rs, rounds * 16);
+        memcpy(&t->sha, host.data() + off_tr, sizeof(DevTranscript));
+        return ML_OK;
+    }
     hfe prev = hfe_load(sum);
     std::vector<hfe> evals(td + 1), coeffs;
     for (size_t k = 0; k < rounds; k++) {

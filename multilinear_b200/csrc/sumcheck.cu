@@ -132,14 +132,6 @@ __global__ void __launch_bounds__(SC_THREADS) sumcheck_fold_sums_kernel(fe* __re
 //     comp(x) = sum_t coef[t] * prod_{k < len[t]} x[cols[off[t] + k]]
 // (the C-ABI stand-in for the reference's closure argument, sumcheck.rs:176).  Terms live in shared memory; a thread
 // interpolates one row pair, evaluates the composition and accumulates comp * delta unreduced.
-struct WTerms {
-    const fe* coef;
-    const uint32_t* len;
-    const uint32_t* off;
-    const uint32_t* cols;
-    int n_terms, n_cols;
-};
-static const int W_MAX_WIDTH = 16, W_MAX_TERMS = 64, W_MAX_COLS = 256;
 __global__ void __launch_bounds__(SC_THREADS) wsumcheck_partial_kernel(const fe* __restrict__ m, const fe* __restrict__ d, size_t off, int width,
                                                                        fe r, fe sm1, int is_one, WTerms terms, fe* __restrict__ partials) {
     __shared__ fe scratch[32];
@@ -222,7 +214,9 @@ __global__ void __launch_bounds__(SC_THREADS) wsumcheck_points_kernel(const fe* 
     }
 }
 // fold (:234-247): rows i < off of the matrix and of delta, x <- x + r (x[i+off] - x)
-__global__ void __launch_bounds__(256) wsumcheck_fold_kernel(fe* __restrict__ m, fe* __restrict__ d, size_t off, int width, fe r) {
+__global__ void __launch_bounds__(256) wsumcheck_fold_kernel(fe* __restrict__ m, fe* __restrict__ d, size_t off, int width, fe r,
+                                                             const fe* __restrict__ r_dev) {
+    if (r_dev) r = fe_load(r_dev);
     size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t total = off * (size_t)(width + 1);
@@ -236,6 +230,7 @@ __global__ void __launch_bounds__(256) wsumcheck_fold_kernel(fe* __restrict__ m,
     }
 }
 
+static inline fe fe_zero_host() { fe z; z.v[0] = z.v[1] = z.v[2] = z.v[3] = 0u; return z; }
 static inline unsigned blocks_for(size_t n) {
     size_t b = (n + SC_THREADS - 1) / SC_THREADS;
     if (b > (size_t)SC_MAX_BLOCKS) b = SC_MAX_BLOCKS;
@@ -360,8 +355,32 @@ int wsumcheck_fold_launch(fe* m, fe* d, size_t height, size_t width, hfe r, cuda
     if (half == 0) return ML_OK;
     size_t total = half * (width + 1), blocks = (total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    wsumcheck_fold_kernel<<<(unsigned)blocks, 256, 0, s>>>(m, d, half, (int)width, to_dev_fe_h(r));
+    wsumcheck_fold_kernel<<<(unsigned)blocks, 256, 0, s>>>(m, d, half, (int)width, to_dev_fe_h(r), nullptr);
     MLB_KERNEL_CHECK();
+    return ML_OK;
+}
+int wsumcheck_fold_dev_launch(fe* m, fe* d, size_t height, size_t width, const fe* r_dev, cudaStream_t s) {
+    const size_t half = height >> 1;
+    if (half == 0) return ML_OK;
+    size_t total = half * (width + 1), blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wsumcheck_fold_kernel<<<(unsigned)blocks, 256, 0, s>>>(m, d, half, (int)width, fe_zero_host(), r_dev);
+    MLB_KERNEL_CHECK();
+    return ML_OK;
+}
+int wsumcheck_points_partials_launch(const fe* m, const fe* d, size_t height, size_t width, const WTerms& t, int td, fe* partials, int* n_blocks,
+                                     cudaStream_t s) {
+    if (td < 1 || td > W_MAX_TD) return ML_ERR_ARG;
+    const size_t half = height >> 1;
+    const unsigned nb = blocks_for(half);
+    switch (td) {
+        case 1: wsumcheck_points_kernel<1><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+        case 2: wsumcheck_points_kernel<2><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+        case 3: wsumcheck_points_kernel<3><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+        default: wsumcheck_points_kernel<4><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+    }
+    MLB_KERNEL_CHECK();
+    *n_blocks = (int)nb;
     return ML_OK;
 }
 }  // namespace mlb
