@@ -336,10 +336,59 @@ class BatchedPCSProof {
     BatchedPCSProof(BatchedPCSProof&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
     ~BatchedPCSProof() { if (h_) ml_bpcs_proof_free(h_); }
     int verify(Transcript& t) const { return ml_batched_pcs_verify(h_, t.handle()); }  // :182-253
+    std::vector<uint8_t> fri_proof_bytes() const {  // bincode layout of the BatchedFriProof (see ml_bfri_proof_serialize)
+        const ml_bfri_proof* f = ml_bpcs_proof_fri(h_);
+        std::vector<uint8_t> out(ml_bfri_proof_serialized_len(f));
+        check(ml_bfri_proof_serialize(f, out.data()));
+        return out;
+    }
 
   private:
+    friend class ShardedBatchedProver;
     BatchedPCSProof() = default;
     ml_bpcs_proof* h_ = nullptr;
 };
+// BatchedPCSProof::prove over several GPUs from one process (ml_shard_*, csrc/shard.cu); `devices` may repeat (virtual ranks)
+class ShardedBatchedProver {
+  public:
+    ShardedBatchedProver(const std::vector<int>& devices, size_t n_polys, size_t n_vars) {
+        std::vector<int> ranks(devices.size());
+        for (size_t i = 0; i < ranks.size(); i++) ranks[i] = (int)i;
+        check(ml_shard_create((int)devices.size(), (int)devices.size(), ranks.data(), devices.data(), n_polys, n_vars, &h_));
+    }
+    ShardedBatchedProver(const ShardedBatchedProver&) = delete;
+    ~ShardedBatchedProver() { if (h_) ml_shard_free(h_); }
+    BatchedPCSProof prove(const BatchedPCSClaim& claim, const std::vector<MultilinearPolynomialEvals>& polys, Transcript& t) {
+        std::vector<const uint8_t*> ptrs;
+        for (auto& p : polys) ptrs.push_back(raw(p.evals));
+        BatchedPCSProof p;
+        check(ml_shard_batched_pcs_prove(h_, raw(claim.inputs), claim.inputs.size(), raw(claim.outputs), polys.size(), ptrs.data(), t.handle(), &p.h_));
+        return p;
+    }
+
+  private:
+    ml_shard* h_ = nullptr;
+};
+
+// src/polynomials.rs:3-98 — univariate helpers over the domain 0..n-1 (named Univariate* here: `Polynomial` above is src/ntt's)
+struct UnivariatePolynomialEvals;
+struct UnivariatePolynomial {
+    std::vector<F> coeffs;
+    UnivariatePolynomialEvals evaluate_over_domain() const;  // :16-28
+};
+struct UnivariatePolynomialEvals {
+    std::vector<F> evals;
+    bool operator==(const UnivariatePolynomialEvals& o) const { return evals == o.evals; }
+    UnivariatePolynomial interpolate() const {  // :51-86
+        UnivariatePolynomial p{std::vector<F>(evals.size())};
+        check(ml_poly_interpolate(raw(evals), evals.size(), raw(p.coeffs)));
+        return p;
+    }
+};
+inline UnivariatePolynomialEvals UnivariatePolynomial::evaluate_over_domain() const {
+    UnivariatePolynomialEvals e{std::vector<F>(coeffs.size())};
+    check(ml_poly_evaluate_over_domain(raw(coeffs), coeffs.size(), raw(e.evals)));
+    return e;
+}
 
 }  // namespace ml

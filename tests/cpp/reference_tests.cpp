@@ -115,6 +115,20 @@ static void batched_pcs_verify_test() {
     BatchedPCSProof proof = BatchedPCSProof::prove(claim, polys, transcript);
     Transcript vt;
     EXPECT(proof.verify(vt) == 0);
+    // the same claim through the sharded prover (two virtual ranks on device 0): identical proof bytes, identical transcript
+    ShardedBatchedProver sharded({0, 0}, num_polys, n_vars);
+    Transcript st;
+    BatchedPCSProof sproof = sharded.prove(claim, polys, st);
+    Transcript svt;
+    EXPECT(sproof.verify(svt) == 0);
+    EXPECT(sproof.fri_proof_bytes() == proof.fri_proof_bytes());
+    EXPECT(st.random() == transcript.random());
+}
+// src/polynomials.rs:197-204
+static void interpolation_test() {
+    UnivariatePolynomialEvals evals{{F::from(0), F::from(1), F::from(4), F::from(8), F::from(9), F::from(3)}};
+    UnivariatePolynomial pol = evals.interpolate();
+    EXPECT(evals == pol.evaluate_over_domain());
 }
 
 // ---- field helpers for the verifier-side equations (one-element calls into the library; the host mirror has no arithmetic)
@@ -194,7 +208,8 @@ static void sumcheck_test() {
 int main() {
     struct { const char* name; void (*fn)(); } tests[] = {
         {"intt_test", intt_test}, {"merkle_test", merkle_test}, {"batched_merkle_test", batched_merkle_test},
-        {"multilinear_conversion_test", multilinear_conversion_test}, {"prove_and_verify_test", prove_and_verify_test},
+        {"multilinear_conversion_test", multilinear_conversion_test}, {"interpolation_test", interpolation_test},
+        {"prove_and_verify_test", prove_and_verify_test},
         {"multilinear_pcs_bench_test", multilinear_pcs_bench_test}, {"batched_pcs_verify_test", batched_pcs_verify_test},
         {"sumcheck_test", sumcheck_test}};
     for (auto& t : tests) {
