@@ -198,6 +198,7 @@ def run_batched_commit(torch, ml, L, dist, world, rank, local_rank, n_polys, log
             dist.barrier()
 
     def timed(fn):
+        sync()  # ranks enter together: a peer that is late by more than MLB_SHARD_TIMEOUT_S would read as ML_ERR_PEER
         launches0 = ml.kernel_launches()
         out = fn()  # warm-up: tables, pools
         per_call = ml.kernel_launches() - launches0

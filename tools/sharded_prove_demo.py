@@ -72,6 +72,7 @@ stream = torch.cuda.ExternalStream(sh.stream(0), device=dev)
 
 
 def timed(fn):
+    barrier()
     fn()  # warm-up: tables, pools
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
