@@ -99,9 +99,15 @@ static int staged_upload(void* dst, const void* src, size_t bytes, cudaStream_t 
         }
     };
     std::thread th[STAGE_THREADS - 1];
-    for (int w = 1; w < STAGE_THREADS; w++) th[w - 1] = std::thread(work, w);
+    for (int w = 1; w < STAGE_THREADS; w++) {
+        try {
+            th[w - 1] = std::thread(work, w);
+        } catch (...) {  // no thread to be had: the remaining chunks are picked up by the threads that did start
+        }
+    }
     work(0);
-    for (auto& t : th) t.join();
+    for (auto& t : th)
+        if (t.joinable()) t.join();
     if (status != ML_OK) { set_error("staged upload failed: %s", cudaGetErrorString(cudaGetLastError())); return status; }
     return ML_OK;
 }
