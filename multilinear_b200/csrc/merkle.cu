@@ -11,6 +11,7 @@
 //   - every layer is still written to HBM (the prover opens paths from them), 32 B per digest, once;
 //   - upper layers repeat the same scheme on digests; the last <= 2048 nodes finish in one CTA.
 // All layers live in one buffer: layer l starts at digest index 2L - (2L >> l) (merkle_layer_offset).
+#include <cstdlib>
 #include <cstring>
 #include "field.cuh"
 #include "internal.h"
@@ -235,23 +236,48 @@ __global__ void merkle_bytes_kernel(const uint8_t* const* __restrict__ data, int
     sha_store_digest(layer_ptr(digests, n_items, 0, i), st);
 }
 
+// Subtree depth per thread.  A thread that walks 2^G inputs runs 2^(G+1) - 1 hashes back to back (≈1.9 us per compression when
+// its warp has the SM sub-partition to itself): 8-input walks take 27 us (nodes) / 43 us (leaves) no matter how small the layer is.
+// Shallower walks on small layers (more threads, shorter chains) were measured in round 2 (profiles/r2_serial_latency.txt): one
+// serial 2^24 commit 10.76 -> 10.60 ms with MLB_WALK_MIN_THREADS = 2^15..2^18, at 97-112 launches instead of 76 — every level
+// saved from a walk comes back as a launch gap — so the default stays 0 (always 8-input walks); the knobs remain for experiments:
+// MLB_WALK_MIN_THREADS = threads a launch should keep before the walk gets shallower, MLB_TOP_MAX = nodes handed to the cluster top.
+static size_t env_size(const char* name, size_t dflt) {
+    const char* e = getenv(name);
+    return e ? (size_t)strtoull(e, nullptr, 10) : dflt;
+}
+static int walk_depth(size_t count) {
+    static const size_t min_threads = env_size("MLB_WALK_MIN_THREADS", 0);
+    int g = 3;
+    while (g > 1 && (count >> g) < min_threads) g--;
+    return g;
+}
+static size_t top_max_count() {
+    static const size_t v = env_size("MLB_TOP_MAX", TOP_MAX_COUNT);
+    return v;
+}
 // Layers above `from_layer` (which must be complete).
 static int upper_from(uint8_t* digests, size_t n_leaves, int from_layer, cudaStream_t s) {
     int total = (int)ilog2(n_leaves);
     int layer = from_layer;
     while (layer < total) {
         size_t count = n_leaves >> layer;
-        if (count <= TOP_MAX_COUNT) {
+        if (count <= top_max_count()) {
             ProfScope prof(PROF_MERKLE_TOP, 64.0 * (double)count, s);
             MLB_TRY(merkle_top_launch(digests, n_leaves, layer, s));
             MLB_KERNEL_CHECK();
             return ML_OK;
         }
-        size_t threads = count >> 3;
-        ProfScope prof(PROF_MERKLE_NODES, 60.0 * (double)count, s);  // read 32 B/digest, write 3 layers (28 B/digest)
-        merkle_nodes_kernel<3><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(digests, n_leaves, layer);
+        int g = walk_depth(count);
+        if (layer + g > total) g = total - layer;
+        const size_t threads = count >> g;
+        ProfScope prof(PROF_MERKLE_NODES, 60.0 * (double)count, s);  // read 32 B/digest, write the layers above (<= 28 B/digest)
+        const unsigned grid = (unsigned)((threads + 127) / 128);
+        if (g >= 3) merkle_nodes_kernel<3><<<grid, 128, 0, s>>>(digests, n_leaves, layer);
+        else if (g == 2) merkle_nodes_kernel<2><<<grid, 128, 0, s>>>(digests, n_leaves, layer);
+        else merkle_nodes_kernel<1><<<grid, 128, 0, s>>>(digests, n_leaves, layer);
         MLB_KERNEL_CHECK();
-        layer += 3;
+        layer += g;
     }
     return ML_OK;
 }
@@ -261,13 +287,17 @@ int merkle_rs_launch(const fe* code, size_t n_code, uint8_t* digests, cudaStream
     const size_t L = n_code / 2;
     if (L == 0) return ML_ERR_NOT_POW2;
     if (L >= 8) {
-        size_t threads = L >> 3;
-        {   // read one 32-byte pair per leaf, write layers 0..3 (32 * (1 + 1/2 + 1/4 + 1/8) bytes per leaf)
-            ProfScope prof(PROF_MERKLE_LEAF, 92.0 * (double)L, s);
-            merkle_rs_kernel<3><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(code, L, digests);
+        const int g = walk_depth(L);
+        const size_t threads = L >> g;
+        {   // read one 32-byte pair per leaf, write layers 0..g (32 * (1 + 1/2 + .. + 2^-g) bytes per leaf)
+            ProfScope prof(PROF_MERKLE_LEAF, (32.0 + 64.0 - (64.0 / (double)(1 << g))) * (double)L, s);
+            const unsigned grid = (unsigned)((threads + 127) / 128);
+            if (g >= 3) merkle_rs_kernel<3><<<grid, 128, 0, s>>>(code, L, digests);
+            else if (g == 2) merkle_rs_kernel<2><<<grid, 128, 0, s>>>(code, L, digests);
+            else merkle_rs_kernel<1><<<grid, 128, 0, s>>>(code, L, digests);
             MLB_KERNEL_CHECK();
         }
-        return upper_from(digests, L, 3, s);
+        return upper_from(digests, L, g, s);
     }
     merkle_rs_kernel<0><<<1, 128, 0, s>>>(code, L, digests);
     MLB_KERNEL_CHECK();
