@@ -449,15 +449,21 @@ def run_ours(args):
     # ---- serial pass of the same workload (one commit at a time) with per-kernel CUDA-event timing: per-kernel
     # durations are only well defined when commits do not share the GPU
     ser_steps = max(2, min(args.steps, 5))
-    L.ml_profile_reset()
-    L.ml_profile_enable(1)
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
-    run_steps(ser_steps, which=[0])
+    run_steps(ser_steps, which=[0])  # plain serial pass: the latency of one commit
     s1.record()
     barrier()
     ms_serial = s0.elapsed_time(s1) / ser_steps
+    launches_serial = None
+    l0 = ml.kernel_launches()
+    L.ml_profile_reset()
+    L.ml_profile_enable(1)
+    barrier()
+    run_steps(ser_steps, which=[0])  # the same pass with every kernel group bracketed by CUDA events (adds ≈0.5 ms per commit)
+    barrier()
+    launches_serial = (ml.kernel_launches() - l0) / ser_steps
     L.ml_profile_enable(0)
     kernels = {}
     for i, name in enumerate(PROF_NAMES):
@@ -704,8 +710,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u128", "data": "synthetic",
             "config": workload_config(args),
-            "serial": {"ms_per_commit": ms_serial, "value": world * n / (ms_serial * 1e-3) / 1e6, "unit": UNIT,
-                       "note": "one commit at a time on one stream (latency-bound phases exposed)"},
+            "serial": {"ms_per_commit": ms_serial, "value": world * n / (ms_serial * 1e-3) / 1e6, "unit": UNIT, "launches_per_commit": launches_serial,
+                       "note": "one commit at a time on one stream (latency-bound phases exposed); floor analysis in profiles/r2_serial_latency.txt"},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": world * PE * n / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 16 * n * PE, "d2h_bytes_per_step": blob_len * PE,
                     "polys_in_flight": PE, "numa": numa,
