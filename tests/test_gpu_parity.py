@@ -568,7 +568,7 @@ def test_sharded_batch_commit_single_gpu(ml, oracle, mode):
 
 
 # ------------------------------------------------------------------ sharded BatchedPCSProof::prove (ml_shard_*, config 5)
-@pytest.mark.parametrize("world,nv,B", [(1, 6, 3), (2, 6, 4), (2, 10, 6), (4, 12, 8), (8, 13, 16), (8, 16, 8)])
+@pytest.mark.parametrize("world,nv,B", [(1, 6, 3), (2, 6, 4), (2, 10, 6), (4, 12, 8), (8, 13, 16), (8, 16, 8), (8, 4, 8), (16, 5, 16), (1, 2, 1)])
 def test_sharded_batched_pcs_prove_virtual_ranks_vs_oracle(ml, oracle, world, nv, B):
     """G ranks hosted by one process on ONE GPU (virtual ranks, phases enqueued in lock step): the proof bytes, the sumcheck
     polynomials and the transcript equal the oracle's BatchedPCSProof::prove; so does the unsharded CUDA prover's proof"""
