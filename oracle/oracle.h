@@ -5,7 +5,9 @@
  * `--impl reference` legs may load this library; the product
  * (multilinear_b200/) never links, imports or calls it.
  *
- * PARITY UNPINNED — see oracle/field.h.  Every function cites the reference
+ * PARITY UNPINNED — see oracle/field.h: the reference is Rust, cannot be built in this image and asserts no concrete value.
+ * rust/golden_dump.rs + tests/golden/check_against_rust.py let a maintainer with cargo pin the golden vectors against the crate.
+ * Every function cites the reference
  * file:line whose loop it restates.  Field elements cross the ABI as 16
  * little-endian bytes (src/field.rs:33-38), digests as 32 bytes.
  */
