@@ -28,6 +28,12 @@ int ml_profile_get(int id, double *total_ms, uint64_t *launches, double *alg_byt
 int ml_profile_get_max(int id, double *mean_ms, uint64_t *launches, double *alg_bytes); /* the group's largest launches */
 int ml_microbench(const char *what, size_t n, int iters, double *ms_out, double *work_out);
 
+/* sharded prover (ml_shard_*): device time in ms between the phase marks of the last call on the first local rank's stream —
+ * commit: S0 encode+pack, S1 row subtree, S2 batch root; prove: S0, S1, S2 root + rho, S2 fingerprint partials, S3 reduce,
+ * S4 wait for the matrix, chain incl. S5 first fold, openings + proof (the last three on rank 0 only).  Returns how many. */
+struct ml_shard;
+int ml_shard_phase_ms(const struct ml_shard *sh, double *out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -772,6 +772,12 @@ class ShardedBatchedProver:
     def stream(self, local_index=0):
         return load().ml_shard_stream(self.h, C.c_int(local_index))
 
+    def phase_ms(self):
+        """device time between the phase marks of the last call (instrumentation, multilinear_b200_instr.h)"""
+        out = (C.c_double * 16)()
+        n = load().ml_shard_phase_ms(self.h, out, C.c_int(16))
+        return [out[i] for i in range(n)]
+
     def local_polys(self):
         """global polynomial indices in the order local_evals must be given: for each local rank, rank, rank + world, ..."""
         return [r + l * self.world for r in self.local_ranks for l in range(self.n_polys // self.world)]

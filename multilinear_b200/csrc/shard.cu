@@ -335,6 +335,10 @@ struct ml_shard {
     bool peer_mapped[MAXR];             // opened through IPC (must be closed)
     bool connected = false;
     unsigned long long epoch = 0;
+    // device-time marks of the last call on the first local rank's main stream (include/multilinear_b200_instr.h)
+    static const int N_MARKS = 10;
+    cudaEvent_t mark[N_MARKS] = {nullptr};
+    int n_marks = 0;
     unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
     unsigned pack_ctas = 32;
     ml_shard() {
@@ -481,6 +485,15 @@ int stage_first_fold(ml_shard* sh, ShardRank& r) {
     return signal(sh, r, P6, 0, s);
 }
 
+// phase boundary on the first local rank's main stream
+void mark_phase(ml_shard* sh, int idx) {
+    if (idx >= ml_shard::N_MARKS || sh->local.empty()) return;
+    ShardRank& r = sh->local[0];
+    cudaSetDevice(r.device);
+    if (!sh->mark[idx] && cudaEventCreate(&sh->mark[idx]) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaEventRecord(sh->mark[idx], r.st.main);
+    if (idx + 1 > sh->n_marks) sh->n_marks = idx + 1;
+}
 ShardRank* rank0_of(ml_shard* sh) {
     for (auto& r : sh->local)
         if (r.rank == 0) return &r;
@@ -627,9 +640,24 @@ int ml_shard_create(int world, int n_local, const int* local_ranks, const int* l
     return ML_OK;
 }
 
+// INSTRUMENTATION (include/multilinear_b200_instr.h): device time between the phase marks of the last call on the first local
+// rank's main stream, in ms: commit: [S0 encode+pack, S1 subtree, S2 root]; prove: [S0, S1, S2 root+rho, S2 fingerprint partials,
+// S3 reduce, S4 wait for the matrix (rank 0), chain incl. S5 first fold (rank 0), openings + proof (rank 0)].  Returns the count.
+int ml_shard_phase_ms(const ml_shard* sh, double* out, int cap) {
+    int n = 0;
+    for (int i = 0; i + 1 < sh->n_marks && n < cap; i++) {
+        float ms = 0;
+        if (!sh->mark[i] || !sh->mark[i + 1] || cudaEventElapsedTime(&ms, sh->mark[i], sh->mark[i + 1]) != cudaSuccess) { cudaGetLastError(); ms = -1.f; }
+        out[n++] = ms;
+    }
+    return n;
+}
+
 void ml_shard_free(ml_shard* sh) {
     if (!sh) return;
     DeviceGuard guard;
+    for (int i = 0; i < ml_shard::N_MARKS; i++)
+        if (sh->mark[i]) cudaEventDestroy(sh->mark[i]);
     for (auto& r : sh->local) free_rank(r);
     if (!sh->local.empty()) cudaSetDevice(sh->local[0].device);
     for (int g = 0; g < MAXR; g++)
@@ -698,9 +726,11 @@ int ml_shard_batch_commit_dev(ml_shard* sh, const void* const* local_evals_dev, 
     sh->epoch++;
     const size_t ppr = sh->polys_per_rank;
     for (size_t i = 0; i < sh->local.size(); i++) MLB_TRY(upload_inputs(sh, sh->local[i], nullptr, nullptr, local_evals_dev + i * ppr));
-    for (size_t i = 0; i < sh->local.size(); i++) MLB_TRY(stage_encode_pack(sh, sh->local[i], local_evals_dev + i * ppr));
-    for (auto& r : sh->local) MLB_TRY(stage_subtree(sh, r));
-    for (auto& r : sh->local) MLB_TRY(stage_root(sh, r, false));
+    sh->n_marks = 0;
+    mark_phase(sh, 0);
+    for (size_t i = 0; i < sh->local.size(); i++) { MLB_TRY(stage_encode_pack(sh, sh->local[i], local_evals_dev + i * ppr)); if (i == 0) mark_phase(sh, 1); }
+    for (size_t i = 0; i < sh->local.size(); i++) { MLB_TRY(stage_subtree(sh, sh->local[i])); if (i == 0) mark_phase(sh, 2); }
+    for (size_t i = 0; i < sh->local.size(); i++) { MLB_TRY(stage_root(sh, sh->local[i], false)); if (i == 0) mark_phase(sh, 3); }
     int st = ML_OK;
     for (auto& r : sh->local) {
         MLB_CUDA(cudaSetDevice(r.device));
@@ -743,16 +773,24 @@ int ml_shard_batched_pcs_prove_dev(ml_shard* sh, const uint8_t* inputs, size_t n
     }
     struct ScGuard { ml_sumcheck* p; ~ScGuard() { free_sumcheck(p); } } sc_guard{sc};
 
-    for (size_t i = 0; i < sh->local.size(); i++) MLB_TRY(stage_encode_pack(sh, sh->local[i], local_evals_dev + i * ppr));  // S0
-    for (auto& r : sh->local) MLB_TRY(stage_subtree(sh, r));                                                                // S1
-    for (auto& r : sh->local) { MLB_TRY(stage_root(sh, r, true)); MLB_TRY(stage_fp_partial(sh, r)); }                       // S2
-    for (auto& r : sh->local) MLB_TRY(stage_fp_reduce(sh, r));                                                              // S3
+    sh->n_marks = 0;
+    mark_phase(sh, 0);
+    for (size_t i = 0; i < sh->local.size(); i++) { MLB_TRY(stage_encode_pack(sh, sh->local[i], local_evals_dev + i * ppr)); if (i == 0) mark_phase(sh, 1); }  // S0
+    for (size_t i = 0; i < sh->local.size(); i++) { MLB_TRY(stage_subtree(sh, sh->local[i])); if (i == 0) mark_phase(sh, 2); }                                  // S1
+    for (size_t i = 0; i < sh->local.size(); i++) {                                                                                                              // S2
+        MLB_TRY(stage_root(sh, sh->local[i], true));
+        if (i == 0) mark_phase(sh, 3);
+        MLB_TRY(stage_fp_partial(sh, sh->local[i]));
+        if (i == 0) mark_phase(sh, 4);
+    }
+    for (size_t i = 0; i < sh->local.size(); i++) { MLB_TRY(stage_fp_reduce(sh, sh->local[i])); if (i == 0) mark_phase(sh, 5); }                               // S3
 
     int st = ML_OK;
     if (r0) {
         MLB_CUDA(cudaSetDevice(r0->device));
         cudaStream_t s = r0->st.main;
         MLB_TRY(wait(sh, *r0, P4, -1, s));  // S4: the sumcheck matrix is complete
+        if (r0 == &sh->local[0]) mark_phase(sh, 6);
         ml_fri* fri = new ml_fri();
         fri->log_n0 = (int)ilog2(domain);
         fri->stream = s;
@@ -772,10 +810,12 @@ int ml_shard_batched_pcs_prove_dev(ml_shard* sh, const uint8_t* inputs, size_t n
         const size_t num_steps = ilog2(domain) - ML_LOG_BLOWUP;  // :90
         p->sumcheck.resize(2 * num_steps);
         st = fold_chain_dev(r0->ctx, fri, &hooks, sc, 0, p->sumcheck.data(), 0, false, t, s);  // :100-123
+        if (r0 == &sh->local[0]) mark_phase(sh, 7);
         uint8_t batch_root[32];
         if (st == ML_OK) st = d2h_sync(batch_root, r0->arena + sh->lay.root_out, 32, s);
         if (st == ML_OK) st = read_status(sh, *r0);
         if (st == ML_OK) st = shard_assemble(sh, *r0, fri, t, &p->fri, batch_root);              // :155-173
+        if (r0 == &sh->local[0]) mark_phase(sh, 8);
         free_fri(fri);
         if (st == ML_OK) {  // final transcript to everybody; also releases the other ranks' buffers for the next call
             Scratch trd(s);

@@ -90,6 +90,7 @@ def timed(fn):
 
 
 commit_ms, root = timed(lambda: sh.batch_commit_dev(ptrs))
+commit_phases = sh.phase_ms()
 state = {}
 
 
@@ -101,6 +102,7 @@ def prove():
 
 
 prove_ms, proof = timed(prove)
+prove_phases = sh.phase_ms()
 # every rank's transcript must end in rank 0's final state
 tr = torch.tensor(list(state["t"]), dtype=torch.uint8, device=dev)
 if world > 1:
@@ -126,7 +128,10 @@ if rank == 0:
     line = {"workload": "sharded_batched_pcs_prove", "n_gpus": world, "polys": B, "n_vars": nv, "commit_ms": commit_ms, "prove_ms": prove_ms,
             "commit_melem_per_s": B * n / (commit_ms * 1e-3) / 1e6, "root": root.hex(), "root_matches_oracle_fixture": fixture,
             "proof_bytes": len(blob), "proof_sha256": hashlib.sha256(blob).hexdigest(), "verifies": proof.verify(ml.Transcript()) == 0,
-            "transcripts_agree": transcripts_agree, "arena_bytes_per_rank": L.ml_shard_arena_bytes(sh.h)}
+            "transcripts_agree": transcripts_agree, "arena_bytes_per_rank": L.ml_shard_arena_bytes(sh.h),
+            "rank0_commit_phase_ms": dict(zip(["S0_encode_pack", "S1_row_subtree", "S2_batch_root"], commit_phases)),
+            "rank0_prove_phase_ms": dict(zip(["S0_encode_pack", "S1_row_subtree", "S2_root_rho", "S2_fingerprint_partials", "S3_reduce", "S4_wait_matrix",
+                                              "chain_incl_first_fold", "openings_proof"], prove_phases))}
     if check == "oracle":
         from oracle.binding import Oracle
         O = Oracle(threads=os.cpu_count() or 1)
