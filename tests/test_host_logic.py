@@ -76,3 +76,67 @@ def test_compute_entry_points_fail_loudly_without_gpu(ml):
         assert e.code == 6  # ML_ERR_CUDA: no CPU fallback
     else:
         raise AssertionError("ntt ran without a GPU")
+
+
+def test_host_verifier_accepts_oracle_proof_and_rejects_tampering(ml, oracle):
+    """the C++ verifier behind the ABI (ml_fri_verify, src/fri/mod.rs:287-340) is host code: a proof made by the CPU oracle,
+    handed over as its bincode bytes (ml_fri_proof_deserialize), must verify; tampered copies must fail with the FriProofError code"""
+    from oracle.binding import fe_ints
+    log_n = 6
+    coeffs = oracle.synthetic(17, 1 << log_n)
+    gp = oracle.pow2_generator_powers(log_n + 1)
+    code = oracle.reed_solomon(coeffs, fe_ints(gp[1:2])[0])
+    oproof, st = oracle.fri_prove(code, gp, oracle.transcript())
+    assert st == 0
+    blob = bytes(oproof.blob)
+    p = ml.FriProof.deserialize(blob)
+    assert p.verify() == 0 and p.serialize() == blob
+    assert [c.hex() for c in p.commitments] == [blob[8 + 32 * i:8 + 32 * (i + 1)].hex() for i in range(log_n)]
+    b = bytearray(blob); b[-1] ^= 1
+    assert ml.FriProof.deserialize(b).verify() == 106                      # IncompatibleLastRandom
+    q0 = 8 + 32 * log_n + 8
+    b = bytearray(blob); b[q0 + 8 + 8] ^= 1                                 # first opened value of the first query
+    assert ml.FriProof.deserialize(b).verify() == 104                      # IncompatibleHash
+    b = bytearray(blob[:q0 - 8] + (5).to_bytes(8, "little") + blob[q0:])    # claims 5 queries
+    try:
+        r = ml.FriProof.deserialize(b).verify()
+    except ml.MlError:
+        r = "malformed"
+    assert r in (102, "malformed")
+    for bad in (blob[:-1], blob + b"\0", b""):
+        try:
+            ml.FriProof.deserialize(bad)
+        except ml.MlError as e:
+            assert e.code == 8
+        else:
+            raise AssertionError("malformed proof accepted")
+
+
+def test_interpolate_is_host_code_and_matches_oracle(ml, oracle):
+    """PolynomialEvals::interpolate (src/polynomials.rs:51-86) runs on host scalars: it must work without a GPU"""
+    from oracle.binding import fe_ints
+    for n in (1, 2, 3, 4, 9, 33):
+        e = oracle.synthetic(800 + n, n)
+        c = ml.PolynomialEvals(e).interpolate()
+        assert np.array_equal(c.coeffs, oracle.interpolate(e)), n
+        xs = fe_ints(c.coeffs)
+        for i in (0, n - 1):
+            assert P.poly_eval(xs, i) == fe_ints(e)[i]
+
+
+def test_sharded_prover_argument_checks_without_gpu(ml):
+    import torch
+    for world, n_polys, n_vars in ((3, 6, 8), (2, 3, 8), (4, 4, 1), (32, 32, 8)):   # not a power of two / uneven split / < 2 rows / too many ranks
+        try:
+            ml.ShardedBatchedProver.single_process([0] * world, n_polys, n_vars)
+        except ml.MlError as e:
+            assert e.code in (2, 8), (world, e.code)
+        else:
+            raise AssertionError("bad shape accepted")
+    if not torch.cuda.is_available():
+        try:
+            ml.ShardedBatchedProver.single_process([0, 0], 4, 6)
+        except ml.MlError as e:
+            assert e.code in (6, 7)  # no device: fails loudly, no CPU fallback
+        else:
+            raise AssertionError("sharded prover created without a GPU")
