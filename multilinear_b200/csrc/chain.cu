@@ -298,96 +298,145 @@ int chain_sumcheck_tail_launch(fe* m, fe* d, size_t height, fe* prev, DevTranscr
 }
 
 // ------------------------------------------------------------------ width-w sumcheck rounds (sumcheck.rs:174-202) on the device
-// thread 0: evals[1..td] (sums over CTAs or over the block) -> evals[0] = prev - evals[1] (:188) -> coefficients through the
-// precomputed Lagrange matrix over x = 0..td (interpolate, :189-192) -> absorb coeffs[1..] (:193-197) -> r (:198) -> prev = p(r) (:199)
-__device__ __forceinline__ fe wchain_round_tail(const fe* ev /* td values, points 1..td */, int td, const fe* __restrict__ lag, fe prev,
-                                                DevTranscript* t, fe* coef_out, fe* prev_out) {
-    fe y[W_MAX_TD + 1], c[W_MAX_TD + 1];
-    y[0] = fe_sub(prev, ev[0]);
-    for (int k = 0; k < td; k++) y[k + 1] = ev[k];
-    const int n = td + 1;
-    for (int i = 0; i < n; i++) {
-        fe acc = fe_zero();
-        for (int j = 0; j < n; j++) acc = fe_add(acc, fe_mul(fe_load(lag + i * n + j), y[j]));
-        c[i] = acc;
+// Round bookkeeping by the first warp: evals[1..td] (already summed) -> evals[0] = prev - evals[1] (:188) -> coefficients through
+// the precomputed Lagrange matrix over x = 0..td (interpolate, :189-192; lane i*n + j multiplies lag[i][j] * y[j], row sums by
+// shuffles) -> lane 0: absorb coeffs[1..] (:193-197) -> r (:198) -> prev = p(r) (:199).  `lag_sh` and `ev` live in shared memory.
+// Returns r (valid in lane 0); writes coef_out[0..td) and *prev_io from lane 0.
+__device__ __forceinline__ fe wchain_round_warp(const fe* ev /* shared: td values, points 1..td */, int td, const fe* lag_sh /* shared (td+1)^2 */,
+                                                fe* prev_io /* shared */, DevTranscript* t /* lane 0's */, fe* coef_out) {
+    const int lane = threadIdx.x & 31, n = td + 1;
+    const int i = lane / n, j = lane - i * n;
+    fe term = fe_zero();
+    if (lane < n * n) {
+        const fe y = j == 0 ? fe_sub(*prev_io, ev[0]) : ev[j - 1];
+        term = fe_mul(lag_sh[i * n + j], y);
     }
-    for (int i = 1; i < n; i++) { dt_absorb_fe(t, c[i]); fe_store(coef_out + (i - 1), c[i]); }
-    const fe r = dt_challenge(t);
-    fe acc = c[n - 1];
-    for (int i = n - 2; i >= 0; i--) acc = fe_add(fe_mul(acc, r), c[i]);
-    *prev_out = acc;
+    // row sum over j: lanes i*n .. i*n + n - 1 (n <= 5)
+    fe acc = term;
+    for (int d = 1; d < n; d++) {
+        fe o;
+#pragma unroll
+        for (int k = 0; k < 4; k++) o.v[k] = __shfl_down_sync(0xffffffffu, term.v[k], d);
+        if (j + d < n) acc = fe_add(acc, o);
+    }
+    // coefficient c_i now sits in lane i*n; bring c_0..c_td to lane 0
+    fe c[W_MAX_TD + 1];
+#pragma unroll
+    for (int q = 0; q <= W_MAX_TD; q++) {
+        const int src = q <= td ? q * n : 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) c[q].v[k] = __shfl_sync(0xffffffffu, acc.v[k], src);
+    }
+    fe r = fe_zero();
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 1; q <= W_MAX_TD; q++)
+            if (q <= td) { dt_absorb_fe(t, c[q]); fe_store(coef_out + (q - 1), c[q]); }
+        r = dt_challenge(t);
+        fe v = fe_zero();
+#pragma unroll
+        for (int q = W_MAX_TD; q >= 0; q--)
+            if (q <= td) v = fe_add(fe_mul(v, r), c[q]);
+        *prev_io = v;
+    }
     return r;
 }
 __global__ void __launch_bounds__(256) wchain_finish_kernel(const fe* __restrict__ partials, int nb, int td, const fe* __restrict__ lag, fe* prev,
                                                             DevTranscript* tr, fe* coef_out, fe* r_store, fe* r_dev) {
     __shared__ fe scratch[32];
-    __shared__ fe ev[W_MAX_TD];
+    __shared__ fe ev[W_MAX_TD], lag_sh[(W_MAX_TD + 1) * (W_MAX_TD + 1)], sh_prev;
+    __shared__ DevTranscript sh_tr;
+    const int n = td + 1;
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + n * n) lag_sh[threadIdx.x - 64] = fe_load(lag + (threadIdx.x - 64));
+    if (threadIdx.x == 128) sh_prev = fe_load(prev);
+    if (threadIdx.x >= 160 && threadIdx.x < 160 + (int)(sizeof(DevTranscript) / 4))
+        reinterpret_cast<uint32_t*>(&sh_tr)[threadIdx.x - 160] = reinterpret_cast<const uint32_t*>(tr)[threadIdx.x - 160];
     for (int k = 0; k < td; k++) {
         fe a = fe_zero();
         for (int b = threadIdx.x; b < nb; b += blockDim.x) a = fe_add(a, partials[(size_t)b * td + k]);
         a = block_sum(a, scratch);
         if (threadIdx.x == 0) ev[k] = a;
     }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    DevTranscript t;
+    if (threadIdx.x == 0) t = sh_tr;
+    const fe r = wchain_round_warp(ev, td, lag_sh, &sh_prev, &t, coef_out);
     if (threadIdx.x != 0) return;
-    DevTranscript t = *tr;
-    fe np;
-    const fe r = wchain_round_tail(ev, td, lag, fe_load(prev), &t, coef_out, &np);
-    fe_store(prev, np);
+    fe_store(prev, sh_prev);
     fe_store(r_store, r);
     fe_store(r_dev, r);
     *tr = t;
 }
 // every remaining round of small width-w tables in one CTA: points 1..td in one pass per round (row_{r+1} = row_r + (x1 - x0)),
-// round bookkeeping on thread 0, fold, repeat
+// round bookkeeping on the first warp, fold, repeat.  WMAX bounds the row arrays (4 keeps them in registers for narrow traces).
+template <int WMAX>
 __global__ void __launch_bounds__(512, 1) wchain_tail_kernel(fe* m, fe* d, size_t height, int width, WTerms terms, int td, const fe* __restrict__ lag,
-                                                              fe* prev, DevTranscript* trp, fe* coef_out, fe* rs_out) {
+                                                             fe* prev, DevTranscript* trp, fe* coef_out, fe* rs_out) {
     __shared__ DevTranscript tr;
-    __shared__ fe sh_r, sh_prev, scratch[32], ev[W_MAX_TD];
+    __shared__ fe sh_r, sh_prev, scratch[32], ev[W_MAX_TD], lag_sh[(W_MAX_TD + 1) * (W_MAX_TD + 1)];
     __shared__ fe t_coef[W_MAX_TERMS];
     __shared__ uint32_t t_len[W_MAX_TERMS], t_off[W_MAX_TERMS], t_cols[W_MAX_COLS];
     const int tid = threadIdx.x, nthreads = blockDim.x;
     for (int t = tid; t < terms.n_terms; t += nthreads) { t_coef[t] = terms.coef[t]; t_len[t] = terms.len[t]; t_off[t] = terms.off[t]; }
     for (int c = tid; c < terms.n_cols; c += nthreads) t_cols[c] = terms.cols[c];
+    if (tid < (td + 1) * (td + 1)) lag_sh[tid] = fe_load(lag + tid);
     if (tid == 0) { tr = *trp; sh_prev = fe_load(prev); }
     __syncthreads();
     int round = 0;
     for (size_t h = height; h > 1; h >>= 1, round++) {
         const size_t off = h >> 1;
         fe_acc a[W_MAX_TD];
+#pragma unroll
         for (int k = 0; k < W_MAX_TD; k++) acc_zero(a[k]);
         for (size_t i = tid; i < off; i += nthreads) {
-            fe row[W_MAX_WIDTH], diff[W_MAX_WIDTH];
-            for (int j = 0; j < width; j++) {
-                fe x0 = fe_load(m + i * width + j), x1 = fe_load(m + (i + off) * width + j);
-                row[j] = x1;
-                diff[j] = fe_sub(x1, x0);
+            fe row[WMAX], diff[WMAX];
+#pragma unroll
+            for (int j = 0; j < WMAX; j++) {
+                if (j < width) {
+                    fe x0 = fe_load(m + i * width + j), x1 = fe_load(m + (i + off) * width + j);
+                    row[j] = x1;
+                    diff[j] = fe_sub(x1, x0);
+                }
             }
             fe d0 = fe_load(d + i), dd = fe_load(d + i + off);
             const fe ddiff = fe_sub(dd, d0);
-            for (int k = 0; k < td; k++) {
-                fe comp = fe_zero();
-                for (int t = 0; t < terms.n_terms; t++) {
-                    fe p = t_coef[t];
-                    for (uint32_t c = 0; c < t_len[t]; c++) p = fe_mul(p, row[t_cols[t_off[t] + c]]);
-                    comp = fe_add(comp, p);
-                }
-                acc_mul_add(a[k], comp, dd);
-                if (k + 1 < td) {
-                    for (int j = 0; j < width; j++) row[j] = fe_add(row[j], diff[j]);
-                    dd = fe_add(dd, ddiff);
+#pragma unroll
+            for (int k = 0; k < W_MAX_TD; k++) {
+                if (k < td) {
+                    fe comp = fe_zero();
+                    for (int t = 0; t < terms.n_terms; t++) {
+                        fe p = t_coef[t];
+                        for (uint32_t c = 0; c < t_len[t]; c++) {
+                            const uint32_t col = t_cols[t_off[t] + c];
+                            fe x = row[0];
+#pragma unroll
+                            for (int j = 1; j < WMAX; j++) x = col == (uint32_t)j ? row[j] : x;  // select chain: keeps `row` in registers
+                            p = fe_mul(p, x);
+                        }
+                        comp = fe_add(comp, p);
+                    }
+                    acc_mul_add(a[k], comp, dd);
+                    if (k + 1 < td) {
+#pragma unroll
+                        for (int j = 0; j < WMAX; j++)
+                            if (j < width) row[j] = fe_add(row[j], diff[j]);
+                        dd = fe_add(dd, ddiff);
+                    }
                 }
             }
         }
-        for (int k = 0; k < td; k++) {
-            fe sk = block_sum(acc_reduce(a[k]), scratch);
-            if (tid == 0) ev[k] = sk;
+#pragma unroll
+        for (int k = 0; k < W_MAX_TD; k++) {
+            if (k < td) {
+                fe sk = block_sum(acc_reduce(a[k]), scratch);
+                if (tid == 0) ev[k] = sk;
+            }
         }
-        if (tid == 0) {
-            fe np;
-            const fe r = wchain_round_tail(ev, td, lag, sh_prev, &tr, coef_out + (size_t)round * td, &np);
-            sh_prev = np;
-            sh_r = r;
-            fe_store(rs_out + round, r);
+        __syncthreads();
+        if (tid < 32) {
+            const fe r = wchain_round_warp(ev, td, lag_sh, &sh_prev, &tr, coef_out + (size_t)round * td);
+            if (tid == 0) { sh_r = r; fe_store(rs_out + round, r); }
         }
         __syncthreads();
         const fe r = sh_r;
@@ -415,7 +464,8 @@ int wchain_finish_launch(const fe* partials, int nb, int td, const fe* lag, fe* 
 int wchain_tail_launch(fe* m, fe* d, size_t height, int width, const WTerms& t, int td, const fe* lag, fe* prev, DevTranscript* tr, fe* coef_out,
                        fe* rs_out, cudaStream_t s) {
     ProfScope prof(PROF_TAIL, 0.0, s);
-    wchain_tail_kernel<<<1, 512, 0, s>>>(m, d, height, width, t, td, lag, prev, tr, coef_out, rs_out);
+    if (width <= 4) wchain_tail_kernel<4><<<1, 512, 0, s>>>(m, d, height, width, t, td, lag, prev, tr, coef_out, rs_out);
+    else wchain_tail_kernel<W_MAX_WIDTH><<<1, 512, 0, s>>>(m, d, height, width, t, td, lag, prev, tr, coef_out, rs_out);
     MLB_KERNEL_CHECK();
     return ML_OK;
 }

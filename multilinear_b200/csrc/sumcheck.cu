@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(SC_THREADS) wsumcheck_partial_kernel(const fe*
 // All evaluation points r = 1 .. TD of one round in a single pass over the tables (the reference makes one pass per point,
 // sumcheck.rs:185-187).  The interpolated row at integer r is x0 + r (x1 - x0), so consecutive points differ by the row
 // difference: row_1 = x1, row_{r+1} = row_r + (x1 - x0) — additions only, no interpolation multiplies; same for delta.
-template <int TD>
+// NARROW: width <= 4 — the row lives in registers and a column reference is a 4-way select instead of a local-memory lookup
+template <int TD, bool NARROW = false>
 __global__ void __launch_bounds__(SC_THREADS) wsumcheck_points_kernel(const fe* __restrict__ m, const fe* __restrict__ d, size_t off, int width,
                                                                       WTerms terms, fe* __restrict__ partials) {
     __shared__ fe scratch[32];
@@ -183,12 +184,16 @@ __global__ void __launch_bounds__(SC_THREADS) wsumcheck_points_kernel(const fe* 
     for (int k = 0; k < TD; k++) acc_zero(a[k]);
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    constexpr int WM = NARROW ? 4 : W_MAX_WIDTH;
     for (; i < off; i += stride) {
-        fe row[W_MAX_WIDTH], diff[W_MAX_WIDTH];
-        for (int j = 0; j < width; j++) {
-            fe x0 = fe_load_nc(m + i * width + j), x1 = fe_load_nc(m + (i + off) * width + j);
-            row[j] = x1;
-            diff[j] = fe_sub(x1, x0);
+        fe row[WM], diff[WM];
+#pragma unroll
+        for (int j = 0; j < WM; j++) {
+            if (j < width) {
+                fe x0 = fe_load_nc(m + i * width + j), x1 = fe_load_nc(m + (i + off) * width + j);
+                row[j] = x1;
+                diff[j] = fe_sub(x1, x0);
+            }
         }
         fe d0 = fe_load_nc(d + i), dd = fe_load_nc(d + i + off);
         const fe ddiff = fe_sub(dd, d0);
@@ -197,12 +202,24 @@ __global__ void __launch_bounds__(SC_THREADS) wsumcheck_points_kernel(const fe* 
             fe comp = fe_zero();
             for (int t = 0; t < terms.n_terms; t++) {
                 fe p = t_coef[t];
-                for (uint32_t c = 0; c < t_len[t]; c++) p = fe_mul(p, row[t_cols[t_off[t] + c]]);
+                for (uint32_t c = 0; c < t_len[t]; c++) {
+                    const uint32_t col = t_cols[t_off[t] + c];
+                    if (NARROW) {
+                        fe x = row[0];
+#pragma unroll
+                        for (int j = 1; j < 4; j++) x = col == (uint32_t)j ? row[j] : x;
+                        p = fe_mul(p, x);
+                    } else {
+                        p = fe_mul(p, row[col]);
+                    }
+                }
                 comp = fe_add(comp, p);
             }
             acc_mul_add(a[k], comp, dd);
             if (k + 1 < TD) {
-                for (int j = 0; j < width; j++) row[j] = fe_add(row[j], diff[j]);
+#pragma unroll
+                for (int j = 0; j < WM; j++)
+                    if (j < width) row[j] = fe_add(row[j], diff[j]);
                 dd = fe_add(dd, ddiff);
             }
         }
@@ -373,11 +390,20 @@ int wsumcheck_points_partials_launch(const fe* m, const fe* d, size_t height, si
     if (td < 1 || td > W_MAX_TD) return ML_ERR_ARG;
     const size_t half = height >> 1;
     const unsigned nb = blocks_for(half);
-    switch (td) {
-        case 1: wsumcheck_points_kernel<1><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
-        case 2: wsumcheck_points_kernel<2><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
-        case 3: wsumcheck_points_kernel<3><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
-        default: wsumcheck_points_kernel<4><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+    if (width <= 4) {
+        switch (td) {
+            case 1: wsumcheck_points_kernel<1, true><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+            case 2: wsumcheck_points_kernel<2, true><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+            case 3: wsumcheck_points_kernel<3, true><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+            default: wsumcheck_points_kernel<4, true><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+        }
+    } else {
+        switch (td) {
+            case 1: wsumcheck_points_kernel<1><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+            case 2: wsumcheck_points_kernel<2><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+            case 3: wsumcheck_points_kernel<3><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+            default: wsumcheck_points_kernel<4><<<nb, SC_THREADS, 0, s>>>(m, d, half, (int)width, t, partials); break;
+        }
     }
     MLB_KERNEL_CHECK();
     *n_blocks = (int)nb;
