@@ -239,6 +239,19 @@ int ml_fingerprint(const uint8_t r[16], const uint8_t *coeffs, size_t n, uint8_t
 int ml_batched_fri_prove(const uint8_t *const *codes, size_t n_codes, size_t n, const uint8_t *gen_pows, size_t gen_pows_len,
                          ml_transcript *t, ml_bfri_proof **out);                            /* BatchedFriProof::prove batched_fri.rs:286-318 */
 int ml_batched_fri_verify(const ml_bfri_proof *p);                                          /* batched_fri.rs:320-354 */
+/* BatchedFriProverData (batched_fri.rs:9-14) step by step, host transcript — init :41-99, batched_fold_step :101-181 (the
+ * remaining steps are ml_fri_fold_step on ml_bfri_fri_data), fold :183-205 (device transcript), open_query_at :207-225 */
+typedef struct ml_bfri ml_bfri;
+int ml_bfri_init(const uint8_t *const *codes, size_t n_codes, size_t n, ml_transcript *t, ml_bfri **out);
+int ml_bfri_batched_fold_step(ml_bfri *h, const uint8_t *gen_pows, size_t gen_pows_len, const uint8_t r[16], ml_transcript *t);
+int ml_bfri_fold(const uint8_t *gen_pows, size_t gen_pows_len, const uint8_t *const *codes, size_t n_codes, size_t n, ml_transcript *t, ml_bfri **out);
+void ml_bfri_free(ml_bfri *h);
+ml_fri *ml_bfri_fri_data(ml_bfri *h);                   /* borrowed: fold_step / fold_roots / last_element work on it */
+const ml_merkle *ml_bfri_batch_layer(const ml_bfri *h); /* borrowed: root, layers */
+size_t ml_bfri_num_codes(const ml_bfri *h);
+int ml_bfri_fingerprint_r(const ml_bfri *h, uint8_t out[16]);
+int ml_bfri_open_query_at(const ml_bfri *h, size_t index, uint8_t *batch_values /* n_codes*32 */, uint8_t *batch_digests, uint8_t *batch_dirs,
+                          size_t *batch_path_len, uint8_t *values /* trees*32 */, uint8_t *digests, uint8_t *dirs, size_t *path_lens /* trees */);
 void ml_bfri_proof_free(ml_bfri_proof *p);
 int ml_bfri_proof_batch_commitment(const ml_bfri_proof *p, uint8_t out[32]);
 size_t ml_bfri_proof_num_commitments(const ml_bfri_proof *p);

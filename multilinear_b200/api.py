@@ -467,8 +467,8 @@ class FriProof:
 
 
 class FriProverData:
-    def __init__(self, h):
-        self.h = h
+    def __init__(self, h, owned=True, keep=None):
+        self.h, self.owned, self._keep = h, owned, keep  # keep: the owner of a borrowed handle
 
     @staticmethod
     def init(code, transcript):
@@ -538,7 +538,78 @@ class FriProverData:
 
     def __del__(self):
         try:
-            load().ml_fri_free(self.h)
+            if self.owned:
+                load().ml_fri_free(self.h)
+        except Exception:
+            pass
+
+
+class BatchedFriProverData:
+    """BatchedFriProverData (src/fri/batched_fri.rs:9-14, 41-225) step by step"""
+
+    def __init__(self, h, n_codes, n):
+        self.h, self.n_codes, self.n = h, n_codes, n
+
+    @staticmethod
+    def _codes(codes):
+        cs = [as_elems(c) for c in codes]
+        return cs, (C.c_void_p * len(cs))(*[c.ctypes.data for c in cs])
+
+    @staticmethod
+    def init(codes, transcript):
+        cs, ptrs = BatchedFriProverData._codes(codes)
+        h = C.c_void_p()
+        check(load().ml_bfri_init(ptrs, _sz(len(cs)), _sz(cs[0].shape[0] if cs else 0), transcript.h, C.byref(h)))
+        return BatchedFriProverData(h, len(cs), cs[0].shape[0])
+
+    @staticmethod
+    def fold(gen_pows, codes, transcript):
+        cs, ptrs = BatchedFriProverData._codes(codes)
+        gp = as_elems(gen_pows) if gen_pows is not None else None
+        h = C.c_void_p()
+        check(load().ml_bfri_fold(_p(gp) if gp is not None else None, _sz(gp.shape[0] if gp is not None else 0), ptrs, _sz(len(cs)),
+                                  _sz(cs[0].shape[0] if cs else 0), transcript.h, C.byref(h)))
+        return BatchedFriProverData(h, len(cs), cs[0].shape[0])
+
+    def batched_fold_step(self, gen_pows, r, transcript):
+        gp = as_elems(gen_pows) if gen_pows is not None else None
+        rb = _fe1(r)
+        check(load().ml_bfri_batched_fold_step(self.h, _p(gp) if gp is not None else None, _sz(gp.shape[0] if gp is not None else 0), _p(rb), transcript.h))
+
+    @property
+    def fri_data(self):
+        load().ml_bfri_fri_data.restype = C.c_void_p
+        return FriProverData(C.c_void_p(load().ml_bfri_fri_data(self.h)), owned=False, keep=self)
+
+    @property
+    def fingerprint_r(self):
+        out = np.empty(16, dtype=np.uint8)
+        check(load().ml_bfri_fingerprint_r(self.h, _p(out)))
+        return _int(out)
+
+    def batch_root(self):
+        load().ml_bfri_batch_layer.restype = C.c_void_p
+        return Merkle(C.c_void_p(load().ml_bfri_batch_layer(self.h)), 32 * self.n_codes, owned=False).root()
+
+    def open_query_at(self, index):
+        nt = self.fri_data.num_trees()
+        depth = max((self.n // 2).bit_length() - 1, 0)
+        bvals, bdigs = np.empty((self.n_codes, 32), dtype=np.uint8), np.empty((depth + 1, 32), dtype=np.uint8)
+        bdirs, blen = np.empty(depth + 1, dtype=np.uint8), C.c_size_t(0)
+        values, digs = np.empty((max(nt, 1), 32), dtype=np.uint8), np.empty((nt * 48 + 1, 32), dtype=np.uint8)
+        dirs, lens = np.empty(nt * 48 + 1, dtype=np.uint8), (C.c_size_t * max(nt, 1))()
+        check(load().ml_bfri_open_query_at(self.h, _sz(index), _p(bvals), _p(bdigs), _p(bdirs), C.byref(blen), _p(values), _p(digs), _p(dirs), lens))
+        batch_path = (bvals.tobytes(), [(bdigs[i].tobytes(), int(bdirs[i])) for i in range(blen.value)])
+        paths, off = [], 0
+        for j in range(nt):
+            k = lens[j]
+            paths.append((values[j].tobytes(), [(digs[off + i].tobytes(), int(dirs[off + i])) for i in range(k)]))
+            off += k
+        return batch_path, paths
+
+    def __del__(self):
+        try:
+            load().ml_bfri_free(self.h)
         except Exception:
             pass
 

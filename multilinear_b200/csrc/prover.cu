@@ -919,12 +919,10 @@ int bfri_first_fold_dev(Ctx* ctx, BatchedFri* b, const fe* r_dev, fe** next_out,
     *half_n_out = half_n;
     return ML_OK;
 }
-// query phase of BatchedFriProof::prove / BatchedPCSProof::prove (batched_fri.rs:207-225, 296-308)
-int bfri_assemble(BatchedFri* b, ml_transcript* t, ml_bfri_proof* p, cudaStream_t s) {
+// BatchedFriProverData::open_query_at (batched_fri.rs:207-225) for many indices at once
+int bfri_open_queries(BatchedFri* b, const std::vector<size_t>& idx, std::vector<BQueryH>& out, cudaStream_t s) {
     const size_t n = b->n, L = n / 2, B = b->codes.size();
     if (b->fri->layers.empty()) { set_error("open_query_at: no folded layer (domain too small)"); return ML_ERR_OUT_OF_RANGE; }
-    std::vector<size_t> idx;
-    derive_indices(t, n, idx);
     const size_t nq = idx.size();
     // batch layer: values of all codes + path in the batch tree
     std::vector<PathJob> jobs(nq);
@@ -952,14 +950,22 @@ int bfri_assemble(BatchedFri* b, ml_transcript* t, ml_bfri_proof* p, cudaStream_
     for (size_t q = 0; q < nq; q++) sub[q] = idx[q] % (L / 2);  // :217-218
     std::vector<QueryH> qs;
     MLB_TRY(fri_open_queries(b->fri, sub, qs, s));
-    p->queries.resize(nq);
+    out.resize(nq);
     for (size_t q = 0; q < nq; q++) {
-        PathH& bp = p->queries[q].batch_path;
+        PathH& bp = out[q].batch_path;
         bp.value.assign(hv.begin() + q * B * 32, hv.begin() + (q + 1) * B * 32);
         bp.digests.assign(hp.begin() + q * 32 * (size_t)depth, hp.begin() + (q + 1) * 32 * (size_t)depth);
         fill_dirs(bp, idx[q], depth);
-        p->queries[q].query = std::move(qs[q]);
+        out[q].query = std::move(qs[q]);
     }
+    return ML_OK;
+}
+// query phase of BatchedFriProof::prove / BatchedPCSProof::prove (batched_fri.rs:296-308)
+int bfri_assemble(BatchedFri* b, ml_transcript* t, ml_bfri_proof* p, cudaStream_t s) {
+    if (b->fri->layers.empty()) { set_error("open_query_at: no folded layer (domain too small)"); return ML_ERR_OUT_OF_RANGE; }
+    std::vector<size_t> idx;
+    derive_indices(t, b->n, idx);
+    MLB_TRY(bfri_open_queries(b, idx, p->queries, s));
     memcpy(p->batch_commitment, b->batch_layer->root, 32);
     p->commitments.resize(32 * b->fri->layers.size());
     for (size_t j = 0; j < b->fri->layers.size(); j++) memcpy(&p->commitments[32 * j], b->fri->layers[j].tree->root, 32);
@@ -1764,6 +1770,88 @@ int ml_batched_fri_prove(const uint8_t* const* codes, size_t n_codes, size_t n, 
     int st = bfri_assemble(&b, t, p, s);
     if (st != ML_OK) { delete p; return st; }
     *out = p;
+    return ML_OK;
+}
+// ---- BatchedFriProverData step by step (batched_fri.rs:9-14, 41-225): the host-transcript mirror of the struct's own methods
+}  // extern "C"
+struct ml_bfri {
+    mlbp::BatchedFri b;
+};
+static int bfri_upload_codes(ml_bfri* h, const uint8_t* const* codes, size_t n_codes, size_t n, cudaStream_t s) {
+    if (n_codes == 0) { set_error("Codes must not be empty"); return ML_ERR_SIZE; }
+    MLB_TRY(check_code_len(n));
+    h->b.n = n;
+    h->b.stream = s;
+    for (size_t j = 0; j < n_codes; j++) {
+        fe* c;
+        MLB_TRY(pmalloc((void**)&c, n * 16, s));
+        h->b.codes.push_back(c);
+        MLB_TRY(h2d(c, codes[j], n * 16, s));
+    }
+    return ML_OK;
+}
+extern "C" {
+int ml_bfri_init(const uint8_t* const* codes, size_t n_codes, size_t n, ml_transcript* t, ml_bfri** out) {  // init :41-99
+    API_BEGIN
+    cudaStream_t s = lib_stream(ctx);
+    ml_bfri* h = new ml_bfri();
+    int st = bfri_upload_codes(h, codes, n_codes, n, s);
+    if (st == ML_OK) st = bfri_init(&h->b, t, s);
+    if (st != ML_OK) { delete h; return st; }
+    *out = h;
+    return ML_OK;
+}
+int ml_bfri_batched_fold_step(ml_bfri* h, const uint8_t* gen_pows, size_t gen_pows_len, const uint8_t r[16], ml_transcript* t) {  // :101-181
+    API_BEGIN
+    if (gen_pows) MLB_TRY(check_gen_pows(h->b.fri, gen_pows, gen_pows_len));
+    return bfri_batched_fold_step(ctx, &h->b, hfe_load(r), t, lib_stream(ctx));
+}
+int ml_bfri_fold(const uint8_t* gen_pows, size_t gen_pows_len, const uint8_t* const* codes, size_t n_codes, size_t n, ml_transcript* t,
+                 ml_bfri** out) {  // fold :183-205 — transcript advanced on the device, one synchronisation
+    API_BEGIN
+    cudaStream_t s = lib_stream(ctx);
+    if (gen_pows && gen_pows_len != n) { set_error("gen_pows.len() must equal the domain size"); return ML_ERR_SIZE; }
+    ml_bfri* h = new ml_bfri();
+    int st = bfri_upload_codes(h, codes, n_codes, n, s);
+    if (st == ML_OK) st = bfri_init(&h->b, t, s);
+    if (st == ML_OK && gen_pows) st = check_gen_pows(h->b.fri, gen_pows, gen_pows_len);
+    if (st == ML_OK) {
+        ChainHooks hooks;
+        mlbp::BatchedFri* b = &h->b;
+        hooks.first_fold = [=](const fe* r_dev, fe** next, bool* owns) { *owns = true; size_t hn = 0; return bfri_first_fold_dev(ctx, b, r_dev, next, &hn, s); };
+        st = fold_chain_dev(ctx, h->b.fri, &hooks, nullptr, 0, nullptr, 0, false, t, s);
+    }
+    if (st != ML_OK) { delete h; return st; }
+    *out = h;
+    return ML_OK;
+}
+void ml_bfri_free(ml_bfri* h) { delete h; }
+ml_fri* ml_bfri_fri_data(ml_bfri* h) { return h->b.fri; }                     // fri_data (:13), borrowed
+const ml_merkle* ml_bfri_batch_layer(const ml_bfri* h) { return h->b.batch_layer; }       // batch_layer (:11), borrowed
+size_t ml_bfri_num_codes(const ml_bfri* h) { return h->b.codes.size(); }
+int ml_bfri_fingerprint_r(const ml_bfri* h, uint8_t out[16]) { hfe_store(out, h->b.fingerprint_r); return ML_OK; }  // fingerprint_r (:12)
+// open_query_at (:207-225): batch_values n_codes x 32 B, batch path (log2(n/2) digests + dirs), then the FRI query as ml_fri_open_query_at
+int ml_bfri_open_query_at(const ml_bfri* h, size_t index, uint8_t* batch_values, uint8_t* batch_digests, uint8_t* batch_dirs, size_t* batch_path_len,
+                          uint8_t* values, uint8_t* digests, uint8_t* dirs, size_t* path_lens) {
+    API_BEGIN
+    if (index >= h->b.n / 2) { set_error("open_query_at: Index out of bounds"); return ML_ERR_OUT_OF_RANGE; }
+    std::vector<size_t> idx(1, index);
+    std::vector<BQueryH> q;
+    MLB_TRY(bfri_open_queries(const_cast<mlbp::BatchedFri*>(&h->b), idx, q, lib_stream(ctx)));
+    const PathH& bp = q[0].batch_path;
+    memcpy(batch_values, bp.value.data(), bp.value.size());
+    memcpy(batch_digests, bp.digests.data(), bp.digests.size());
+    memcpy(batch_dirs, bp.dirs.data(), bp.dirs.size());
+    *batch_path_len = bp.dirs.size();
+    size_t doff = 0;
+    for (size_t j = 0; j < q[0].query.paths.size(); j++) {
+        const PathH& p = q[0].query.paths[j];
+        memcpy(values + 32 * j, p.value.data(), 32);
+        memcpy(digests + 32 * doff, p.digests.data(), p.digests.size());
+        memcpy(dirs + doff, p.dirs.data(), p.dirs.size());
+        path_lens[j] = p.dirs.size();
+        doff += p.dirs.size();
+    }
     return ML_OK;
 }
 int ml_batched_fri_verify(const ml_bfri_proof* p) {  // batched_fri.rs:320-354

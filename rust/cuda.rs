@@ -23,7 +23,7 @@ use crate::ntt::{LagrangePolynomial, Polynomial};
 use crate::polynomials::{MultilinearPolynomial, MultilinearPolynomialEvals};
 
 macro_rules! opaque { ($($n:ident),*) => { $(#[repr(C)] pub struct $n { _p: [u8; 0] })* } }
-opaque!(MlTranscript, MlMerkle, MlFri, MlFriProof, MlSumcheck, MlWSumcheck, MlPcsProof, MlBfriProof, MlBpcsProof, MlShard);
+opaque!(MlTranscript, MlMerkle, MlFri, MlFriProof, MlSumcheck, MlWSumcheck, MlPcsProof, MlBfriProof, MlBpcsProof, MlShard, MlBfri);
 
 const _: () = assert!(std::mem::size_of::<Field128>() == 16 && std::mem::align_of::<Field128>() == 16);
 const _: () = assert!(std::mem::size_of::<ReedSolomonPair<Field128>>() == 32); // #[repr(C)], src/fri/mod.rs:30-35
@@ -40,6 +40,15 @@ extern "C" {
     pub fn ml_batched_pcs_prove(inputs: *const u8, n_vars: usize, outputs: *const u8, n_polys: usize, evals: *const *const u8, n: usize, t: *mut MlTranscript, out: *mut *mut MlBpcsProof) -> c_int;
     pub fn ml_batched_pcs_prove_dev(inputs: *const u8, n_vars: usize, outputs: *const u8, n_polys: usize, evals_dev: *const *const c_void, n: usize, t: *mut MlTranscript, stream: *mut c_void, out: *mut *mut MlBpcsProof) -> c_int;
     pub fn ml_batched_pcs_verify(p: *const MlBpcsProof, t: *mut MlTranscript) -> c_int;
+    pub fn ml_bfri_batch_layer(h: *const MlBfri) -> *const MlMerkle;
+    pub fn ml_bfri_batched_fold_step(h: *mut MlBfri, gen_pows: *const u8, gen_pows_len: usize, r: *const u8, t: *mut MlTranscript) -> c_int;
+    pub fn ml_bfri_fingerprint_r(h: *const MlBfri, out: *mut u8) -> c_int;
+    pub fn ml_bfri_fold(gen_pows: *const u8, gen_pows_len: usize, codes: *const *const u8, n_codes: usize, n: usize, t: *mut MlTranscript, out: *mut *mut MlBfri) -> c_int;
+    pub fn ml_bfri_free(h: *mut MlBfri);
+    pub fn ml_bfri_fri_data(h: *mut MlBfri) -> *mut MlFri;
+    pub fn ml_bfri_init(codes: *const *const u8, n_codes: usize, n: usize, t: *mut MlTranscript, out: *mut *mut MlBfri) -> c_int;
+    pub fn ml_bfri_num_codes(h: *const MlBfri) -> usize;
+    pub fn ml_bfri_open_query_at(h: *const MlBfri, index: usize, batch_values: *mut u8, batch_digests: *mut u8, batch_dirs: *mut u8, batch_path_len: *mut usize, values: *mut u8, digests: *mut u8, dirs: *mut u8, path_lens: *mut usize) -> c_int;
     pub fn ml_bfri_proof_batch_commitment(p: *const MlBfriProof, out: *mut u8) -> c_int;
     pub fn ml_bfri_proof_commitments(p: *const MlBfriProof, out: *mut u8) -> c_int;
     pub fn ml_bfri_proof_free(p: *mut MlBfriProof);
@@ -358,12 +367,13 @@ pub fn merkle_commit<T: AsRef<[u8]>>(data: Vec<T>) -> Merkle<T> {
     unsafe { ml_merkle_free(h) };
     Merkle { layers, data }
 }
-/// body of `Merkle::<Vec<T>>::batch_commit` (src/merkle_tree/mod.rs:92-131); the reference stores `data` transposed (:118-125)
-pub fn merkle_batch_commit<T: AsRef<[u8]> + Clone>(data: Vec<Vec<T>>) -> Merkle<Vec<T>> {
+/// body of `Merkle::<Vec<T>>::batch_commit` (src/merkle_tree/mod.rs:92-131); `data` stays [batch][index] as the reference keeps it
+/// (`batch_open` extracts the column, :134-175)
+pub fn merkle_batch_commit<T: AsRef<[u8]>>(data: Vec<Vec<T>>) -> Merkle<Vec<T>> {
     assert!(!data.is_empty(), "Data must not be empty");
     let n = data[0].len();
+    assert!(n.is_power_of_two(), "Each batch length must be a power of two");
     assert!(data.iter().all(|b| b.len() == n), "All batches must have the same length");
-    assert!(n.is_power_of_two(), "Batch size must be a power of two");
     let item = data[0][0].as_ref().len();
     let flats: Vec<Vec<u8>> = data.iter().map(|b| b.iter().flat_map(|x| x.as_ref().iter().copied()).collect()).collect();
     let ptrs: Vec<*const u8> = flats.iter().map(|f| f.as_ptr()).collect();
@@ -371,8 +381,7 @@ pub fn merkle_batch_commit<T: AsRef<[u8]> + Clone>(data: Vec<Vec<T>>) -> Merkle<
     check(unsafe { ml_merkle_batch_commit(ptrs.as_ptr(), data.len(), item, n, &mut h) });
     let layers = unsafe { download_layers(h) };
     unsafe { ml_merkle_free(h) };
-    let columns = (0..n).map(|i| data.iter().map(|b| b[i].clone()).collect()).collect();
-    Merkle { layers, data: columns }
+    Merkle { layers, data }
 }
 fn path_from(digests: &[u8], dirs: &[u8]) -> Vec<(HashDigest, Direction)> {
     digests.chunks_exact(32).zip(dirs).map(|(d, &s)| (digest(d), if s == 0 { Direction::Left } else { Direction::Right })).collect()
@@ -560,6 +569,73 @@ pub fn batched_fri_prove(codes: &[Vec<F>], gen_pows: &[F], transcript: &mut Tran
     let proof = unsafe { bfri_proof_from(h) };
     unsafe { ml_bfri_proof_free(h) };
     proof
+}
+/// `BatchedFriProverData<F>` (src/fri/batched_fri.rs:9-14) with the batch layer and every tree resident in HBM:
+/// init :41-99, batched_fold_step :101-181, fold :183-205, open_query_at :207-225; `fri_data()` borrows the inner FriProverData
+pub struct CudaBatchedFriProverData {
+    h: *mut MlBfri,
+}
+impl CudaBatchedFriProverData {
+    pub fn init(codes: &[Vec<F>], transcript: &mut Transcript) -> Self {
+        let ptrs: Vec<*const u8> = codes.iter().map(|c| p(c)).collect();
+        let mut h = std::ptr::null_mut();
+        check(unsafe { ml_bfri_init(ptrs.as_ptr(), codes.len(), codes[0].len(), transcript.h, &mut h) });
+        Self { h }
+    }
+    pub fn batched_fold_step(&mut self, gen_pows: &[F], r: F, transcript: &mut Transcript) {
+        check(unsafe { ml_bfri_batched_fold_step(self.h, p(gen_pows), gen_pows.len(), r.as_ref().as_ptr(), transcript.h) });
+    }
+    /// the remaining steps (`prover_data.fri_data.fold_step(gen_pows, k, r, transcript)`, :198-201)
+    pub fn fold_step(&mut self, gen_pows: &[F], k: usize, r: F, transcript: &mut Transcript) {
+        check(unsafe { ml_fri_fold_step(ml_bfri_fri_data(self.h), p(gen_pows), gen_pows.len(), k, r.as_ref().as_ptr(), transcript.h) });
+    }
+    pub fn fold(gen_pows: &[F], codes: &[Vec<F>], transcript: &mut Transcript) -> Self {
+        let ptrs: Vec<*const u8> = codes.iter().map(|c| p(c)).collect();
+        let mut h = std::ptr::null_mut();
+        check(unsafe { ml_bfri_fold(p(gen_pows), gen_pows.len(), ptrs.as_ptr(), codes.len(), codes[0].len(), transcript.h, &mut h) });
+        Self { h }
+    }
+    pub fn fingerprint_r(&self) -> F {
+        let mut out = zeros(1);
+        check(unsafe { ml_bfri_fingerprint_r(self.h, pm(&mut out)) });
+        out[0]
+    }
+    pub fn batch_root(&self) -> HashDigest {
+        let mut raw = [0u8; 32];
+        check(unsafe { ml_merkle_root(ml_bfri_batch_layer(self.h), raw.as_mut_ptr()) });
+        digest(&raw)
+    }
+    pub fn fold_roots(&self) -> Vec<HashDigest> {
+        let f = unsafe { ml_bfri_fri_data(self.h) };
+        let n = unsafe { ml_fri_num_trees(f) };
+        let mut raw = vec![0u8; 32 * n];
+        check(unsafe { ml_fri_fold_roots(f, raw.as_mut_ptr()) });
+        raw.chunks_exact(32).map(digest).collect()
+    }
+    pub fn open_query_at(&self, index: usize) -> BatchedQueryProof<F> {
+        let f = unsafe { ml_bfri_fri_data(self.h) };
+        let (trees, b) = (unsafe { ml_fri_num_trees(f) }, unsafe { ml_bfri_num_codes(self.h) });
+        let (mut bvals, mut bdigs, mut bdirs, mut blen) = (vec![0u8; 32 * b], vec![0u8; 32 * 64], vec![0u8; 64], 0usize);
+        let (mut values, mut lens) = (vec![0u8; 32 * trees], vec![0usize; trees]);
+        let (mut digests, mut dirs) = (vec![0u8; 32 * 64 * trees], vec![0u8; 64 * trees]);
+        check(unsafe {
+            ml_bfri_open_query_at(self.h, index, bvals.as_mut_ptr(), bdigs.as_mut_ptr(), bdirs.as_mut_ptr(), &mut blen, values.as_mut_ptr(),
+                                  digests.as_mut_ptr(), dirs.as_mut_ptr(), lens.as_mut_ptr())
+        });
+        let pair = |v: &[u8]| ReedSolomonPair { value: fe(&v[..16]), minus_value: fe(&v[16..]) };
+        let batch_path = MerkleInclusionPath { value: bvals.chunks_exact(32).map(pair).collect(), path: path_from(&bdigs[..32 * blen], &bdirs[..blen]) };
+        let (mut paths, mut off) = (Vec::with_capacity(trees), 0);
+        for j in 0..trees {
+            paths.push(MerkleInclusionPath { value: pair(&values[32 * j..32 * j + 32]), path: path_from(&digests[32 * off..32 * (off + lens[j])], &dirs[off..off + lens[j]]) });
+            off += lens[j];
+        }
+        BatchedQueryProof { batch_path, query_proof: QueryProof { paths } }
+    }
+}
+impl Drop for CudaBatchedFriProverData {
+    fn drop(&mut self) {
+        unsafe { ml_bfri_free(self.h) }
+    }
 }
 unsafe fn bpcs_proof_from(h: *mut MlBpcsProof, claim: BatchedPCSClaim<F>) -> BatchedPCSProof<F> {
     let fri_proof = bfri_proof_from(ml_bpcs_proof_fri(h));

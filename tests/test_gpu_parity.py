@@ -446,6 +446,42 @@ def test_batched_golden(ml, golden):
     assert sha(proof.fri_proof.serialize()) == g["blob_sha"] and proof.verify(ml.Transcript()) == 0
 
 
+def test_batched_fri_prover_data_stepwise(ml, oracle):
+    """BatchedFriProverData::{init, batched_fold_step, fold, open_query_at} (batched_fri.rs:41-225) one call at a time with the
+    host transcript, as `fold` (:183-205) sequences them: roots, last element, transcript and openings must equal those of the
+    one-call prover (whose proof is compared with the oracle's)"""
+    log_n, B = 7, 5
+    n = 1 << (log_n + 1)
+    gp = oracle.pow2_generator_powers(log_n + 1)
+    gen = fe_ints(gp[1:2])[0]
+    codes = [oracle.reed_solomon(oracle.synthetic(4000 + j, 1 << log_n), gen) for j in range(B)]
+    t = ml.Transcript()
+    d = ml.BatchedFriProverData.init(codes, t)
+    r = t.next_challenge()
+    d.batched_fold_step(gp, r, t)
+    for k in range(1, log_n):
+        r = t.next_challenge()
+        d.fri_data.fold_step(gp, k, r, t)
+    t2 = ml.Transcript()
+    d2 = ml.BatchedFriProverData.fold(gp, codes, t2)      # the same on the device transcript
+    assert d.fri_data.fold_roots() == d2.fri_data.fold_roots() and d.fri_data.last_element == d2.fri_data.last_element is not None
+    assert d.batch_root() == d2.batch_root() and d.fingerprint_r == d2.fingerprint_r and t.random() == t2.random()
+    ot = oracle.transcript()
+    oproof, st = oracle.batched_fri_prove(codes, gp, ot)
+    assert st == 0
+    proof = ml.BatchedFriProof.prove(codes, gp, ml.Transcript())
+    assert proof.serialize() == oproof.blob
+    assert proof.batch_commitment == d.batch_root() and proof.commitments == d.fri_data.fold_roots() and proof.last_elem == d.fri_data.last_element
+    bp, paths = d.open_query_at(37)
+    bp2, paths2 = d2.open_query_at(37)
+    assert (bp, paths) == (bp2, paths2) and len(bp[0]) == 32 * B and len(bp[1]) == log_n and len(paths) == log_n - 1
+    assert ml.path_verify(bp[0], bp[1], d.batch_root(), 37) == 0
+    sub = 37 % (n // 4)
+    assert paths == d.fri_data.open_query_at(sub)          # :217-218
+    with pytest.raises(ml.MlError):
+        d.open_query_at(n // 2)
+
+
 @pytest.mark.parametrize("nv,B", [(2, 1), (3, 2), (5, 3), (10, 7), (12, 64), (14, 5)])
 def test_batched_pcs_vs_oracle(ml, oracle, nv, B):
     rng = random.Random(nv * 100 + B)
